@@ -1,0 +1,135 @@
+// C ABI (include/ffpa_b200.h): argument validation mirroring the reference launcher's TORCH_CHECK
+// contract (/root/reference/csrc/cuffpa/launch.cuh:79-129, ffpa_api.cc:53-62,180-205), then dispatch
+// to the sm_100a kernels. No torch types, no host synchronisation, no CPU fallback.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "ffpa_internal.h"
+
+namespace ffpa {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int32_t> g_impl_hint{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+static int check_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error(FFPA_ERR_NO_DEVICE, "no CUDA device");
+  static int cc[64] = {0};
+  if (dev >= 0 && dev < 64 && cc[dev] == 0) {
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cc[dev] = major * 10 + minor;
+  }
+  const int c = (dev >= 0 && dev < 64) ? cc[dev] : 0;
+  if (c / 10 != 10)
+    return set_error(FFPA_ERR_NO_DEVICE, "ffpa_b200 needs an sm_100-class GPU (found sm_%d); there is no fallback path", c);
+  return FFPA_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_strides(const char* name, const int64_t* s, const int32_t* dims) {
+  if (s[3] != 1) return set_error(FFPA_ERR_INVALID_ARGUMENT, "%s: last-dim stride must be 1, got %lld", name, (long long)s[3]);
+  for (int i = 0; i < 3; ++i)
+    if (dims[i] > 1 && (s[i] % 8 != 0 || s[i] <= 0))
+      return set_error(FFPA_ERR_INVALID_ARGUMENT, "%s: stride[%d]=%lld must be a positive multiple of 8 elements (16 bytes)", name, i, (long long)s[i]);
+  return FFPA_OK;
+}
+
+}  // namespace ffpa
+
+using namespace ffpa;
+
+extern "C" {
+
+int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream) {
+  if (!p) return set_error(FFPA_ERR_INVALID_ARGUMENT, "params is NULL");
+  if (int e = check_device()) return e;
+  if (!p->q || !p->k || !p->v || !p->o) return set_error(FFPA_ERR_INVALID_ARGUMENT, "q/k/v/o must be non-NULL device pointers");
+  if (p->dtype != FFPA_DTYPE_F16 && p->dtype != FFPA_DTYPE_BF16)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "dtype must be fp16 or bf16");
+  if (p->batch <= 0 || p->heads_q <= 0 || p->heads_kv <= 0 || p->seqlen_q <= 0 || p->seqlen_kv <= 0 || p->head_dim <= 0)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "all sizes must be positive (B=%d Hq=%d Hkv=%d Nq=%d Nkv=%d D=%d)",
+                     p->batch, p->heads_q, p->heads_kv, p->seqlen_q, p->seqlen_kv, p->head_dim);
+  if (p->heads_q % p->heads_kv != 0)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "Q heads (%d) must be an integer multiple of KV heads (%d)", p->heads_q, p->heads_kv);
+  if (p->head_dim % 8 != 0) return set_error(FFPA_ERR_INVALID_ARGUMENT, "head_dim must be a multiple of 8, got %d", p->head_dim);
+  if (p->head_dim > 1024) return set_error(FFPA_ERR_INVALID_ARGUMENT, "head_dim must be <= 1024, got %d", p->head_dim);
+  if (p->causal && p->seqlen_kv < p->seqlen_q)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "causal attention requires Nkv >= Nq (got Nq=%d, Nkv=%d)", p->seqlen_q, p->seqlen_kv);
+  if (p->causal && p->bias_kind != FFPA_BIAS_NONE)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "attn bias and causal masking are mutually exclusive");
+  if (p->bias_kind != FFPA_BIAS_NONE) {
+    if (p->bias_kind != FFPA_BIAS_F32 && p->bias_kind != FFPA_BIAS_QDTYPE)
+      return set_error(FFPA_ERR_INVALID_ARGUMENT, "attn bias dtype must be fp32 or match Q");
+    if (!p->bias) return set_error(FFPA_ERR_INVALID_ARGUMENT, "bias_kind set but bias pointer is NULL");
+    if (p->bias_stride[3] != 1) return set_error(FFPA_ERR_INVALID_ARGUMENT, "attn bias last dim must be contiguous");
+  }
+  if (!(p->dropout_p >= 0.f && p->dropout_p < 1.f))
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "dropout_p must be in [0, 1), got %f", (double)p->dropout_p);
+  const int32_t qd[3] = {p->batch, p->heads_q, p->seqlen_q};
+  const int32_t kd[3] = {p->batch, p->heads_kv, p->seqlen_kv};
+  if (int e = check_strides("Q", p->q_stride, qd)) return e;
+  if (int e = check_strides("K", p->k_stride, kd)) return e;
+  if (int e = check_strides("V", p->v_stride, kd)) return e;
+  if (int e = check_strides("O", p->o_stride, qd)) return e;
+  if (!aligned16(p->q) || !aligned16(p->k) || !aligned16(p->v) || !aligned16(p->o))
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "q/k/v/o base pointers must be 16-byte aligned");
+  if (p->fp8 || g_impl_hint.load() == FFPA_IMPL_CUTE_TMA_FP4)
+    return set_error(FFPA_ERR_UNSUPPORTED, p->fp8 ? "FP8 forward is not built into this library yet" : "FP4 path is not implemented on sm_100a");
+  if (p->head_dim > 512)
+    return set_error(FFPA_ERR_UNSUPPORTED, "head_dim %d > 512 is not built into this library yet", p->head_dim);
+  return launch_fwd_sm100(*p, static_cast<cudaStream_t>(stream));
+}
+
+int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream) {
+  (void)stream;
+  if (!p) return set_error(FFPA_ERR_INVALID_ARGUMENT, "params is NULL");
+  return set_error(FFPA_ERR_UNSUPPORTED, "backward is not built into this library yet");
+}
+
+uint64_t ffpa_b200_bwd_workspace_bytes(int32_t batch, int32_t heads_q, int32_t heads_kv, int32_t seqlen_q,
+                                       int32_t seqlen_kv, int32_t head_dim) {
+  (void)batch; (void)heads_q; (void)heads_kv; (void)seqlen_q; (void)seqlen_kv; (void)head_dim;
+  return 0;
+}
+
+int ffpa_b200_set_backend_impl(int32_t impl) {
+  if (impl < FFPA_IMPL_AUTO || impl > FFPA_IMPL_CUTE_TMA_FP4)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "backend impl hint %d out of range", impl);
+  g_impl_hint.store(impl);
+  return FFPA_OK;
+}
+int32_t ffpa_b200_get_backend_impl(void) { return g_impl_hint.load(); }
+int32_t ffpa_b200_fwd_available(void) { return 1; }
+int32_t ffpa_b200_bwd_available(void) { return 0; }
+int32_t ffpa_b200_abi_version(void) { return FFPA_B200_ABI_VERSION; }
+uint64_t ffpa_b200_launch_count(void) { return g_launches.load(); }
+const char* ffpa_b200_last_error(void) { return g_err; }
+
+}  // extern "C"

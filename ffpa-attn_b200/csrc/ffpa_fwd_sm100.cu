@@ -1,0 +1,532 @@
+// B200 (sm_100a) Split-D attention forward: tcgen05 MMA into TMEM, TMA loads, 2-CTA cluster,
+// warp-specialised persistent kernel.
+//
+// Replaces the reference's forward kernels behind the same boundary:
+//   /root/reference/csrc/cuffpa/launch.cuh:61-606            (launcher contract / checks)
+//   /root/reference/csrc/cuffpa/native/sm_80/split_d.cuh:85-777 (Split-D algorithm)
+//   /root/reference/csrc/cuffpa/native/prefill.cuh:252-1172  (numerics: mask, online softmax with
+//                                                              lazy rescale, LSE)
+// Design:
+//   * a 2-CTA cluster owns 128 query rows of one (batch, head); CTA r owns rows [64r, 64r+64).
+//   * S = Q K^T  : tcgen05.mma cta_group::2, M=128 N=128, K = head_dim split into 64-wide boxes
+//                  ("Split-D"); each CTA stages its 64 Q rows and its 64 keys of the KV tile.
+//   * O += P V   : tcgen05.mma cta_group::2, M=128 N=256 (head-dim slices), K = 128 keys;
+//                  each CTA stages its P rows and its 128 head-dim columns of V (MN-major).
+//   * accumulators are "lane folded": TMEM lane l of CTA r holds row 64r + l%64, column half l/64.
+//   * warps 0-3 softmax/correction/epilogue, warp 4 MMA issue (leader CTA) + TMEM alloc,
+//     warp 5 TMA producer. mbarrier pipelines: K ring, V ring, S (2), P (2).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cmath>
+#include "ffpa_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace ffpa {
+
+constexpr int kThreads = 192;
+constexpr int kSmemLimit = 232448;
+
+template <int NQK>
+struct FwdCfg {
+  static constexpr int HD = NQK * 64;                     // padded head dim for QK^T
+  static constexpr int DVP = ((HD + 127) / 128) * 128;    // padded head dim for PV / O
+  static constexpr int O_COLS = DVP / 2;                  // TMEM columns of O per CTA (lane folded)
+  static constexpr int NSLICE = (DVP + 255) / 256;        // PV N-slices (256 wide, last may be 128)
+  static constexpr int KST = (NQK + 1) / 2;               // 16 KB K stages per KV tile
+  static constexpr int S_BASE = 256;                      // TMEM column of S[0]; S[1] = +64
+  static constexpr int Q_BYTES = NQK * 8192;
+  static constexpr int P_BYTES = 2 * 16384;
+  static constexpr int NVS = (HD > 256) ? 2 : 3;          // 32 KB V stages
+  static constexpr int kBudget = kSmemLimit - 2048 - 1024;  // static smem + alignment slack
+  static constexpr int kNksRaw = (kBudget - Q_BYTES - P_BYTES - NVS * 32768) / 16384;
+  static constexpr int NKS = kNksRaw > 8 ? 8 : kNksRaw;   // 16 KB K stages
+  static constexpr int SMEM_DYN = Q_BYTES + P_BYTES + NKS * 16384 + NVS * 32768 + 1024;
+  static_assert(NKS >= 2, "not enough shared memory for the K ring");
+  static_assert(O_COLS <= 256, "O does not fit TMEM next to S");
+  __host__ __device__ static constexpr int slice_n(int s) { return (DVP - 256 * s) >= 256 ? 256 : 128; }
+};
+
+struct Barriers {
+  uint64_t q_full, q_empty;
+  uint64_t k_full[8], k_empty[8];
+  uint64_t v_full[3], v_empty[3];
+  uint64_t s_full[2];
+  uint64_t p_full[2], p_empty[2];
+};
+
+__device__ __forceinline__ int num_kv_tiles(const FwdKernelParams& p, int q0) {
+  int tc = (p.seqlen_kv + 127) >> 7;
+  if (p.causal) {
+    int lim = ((q0 + 127 + (p.seqlen_kv - p.seqlen_q)) >> 7) + 1;
+    tc = lim < tc ? lim : tc;
+  }
+  return tc < 1 ? 1 : tc;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr) {
+  // Philox-4x32-10, counter = (ctr_lo, ctr_hi, 0, 0), key = seed. Same generator as
+  // /root/reference/csrc/cuffpa/native/prefill.cuh:398-422 (and curand / torch SDPA).
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0, c3 = 0;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t o0 = c0, o2 = c2;
+    c0 = __umulhi(0xCD9E8D57u, o2) ^ c1 ^ k0;
+    c2 = __umulhi(0xD2511F53u, o0) ^ c3 ^ k1;
+    c1 = 0xCD9E8D57u * o2;
+    c3 = 0xD2511F53u * o0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+template <int NQK, bool BF16, bool DROPOUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, const FwdKernelParams p) {
+  using Cfg = FwdCfg<NQK>;
+  constexpr int CG = 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ Barriers bars;
+  __shared__ float xch[2][128];
+  __shared__ float xl[128];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sP = sQ + Cfg::Q_BYTES;
+  const uint32_t sK = sP + Cfg::P_BYTES;
+  const uint32_t sV = sK + Cfg::NKS * 16384;
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t cluster = blockIdx.x >> 1;
+  const uint32_t nclusters = gridDim.x >> 1;
+
+  auto bar = [](uint64_t& b) { return ptx::smem_u32(&b); };
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar(bars.q_full), 1);
+    ptx::mbar_init(bar(bars.q_empty), 1);
+    for (int i = 0; i < 8; ++i) { ptx::mbar_init(bar(bars.k_full[i]), 1); ptx::mbar_init(bar(bars.k_empty[i]), 1); }
+    for (int i = 0; i < 3; ++i) { ptx::mbar_init(bar(bars.v_full[i]), 1); ptx::mbar_init(bar(bars.v_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar(bars.s_full[i]), 1);
+      ptx::mbar_init(bar(bars.p_full[i]), 8);  // 4 softmax warps x 2 CTAs
+      ptx::mbar_init(bar(bars.p_empty[i]), 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 5 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&map_q);
+    ptx::prefetch_tmap(&map_k);
+    ptx::prefetch_tmap(&map_v);
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc<CG>(ptx::smem_u32(&tmem_slot), 512);
+    ptx::tmem_relinquish<CG>();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const int group = p.heads_q / p.heads_kv;
+
+  if (warp == 5) {
+    // =========================================== TMA producer ===================================
+    if (ptx::elect_one()) {
+      uint32_t kc = 0, vc = 0, it = 0;
+      const uint32_t l_q_full = ptx::mapa(bar(bars.q_full), 0);
+      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters, ++it) {
+        const int mt = item % p.n_mtiles;
+        const int bh = item / p.n_mtiles;
+        const int h = bh % p.heads_q, b = bh / p.heads_q;
+        const int hk = h / group;
+        const int q0 = mt * 128;
+        const int T = num_kv_tiles(p, q0);
+        ptx::mbar_wait(bar(bars.q_empty), (it & 1) ^ 1);
+        if (rank == 0) ptx::mbar_expect_tx(bar(bars.q_full), 2 * Cfg::Q_BYTES);
+#pragma unroll
+        for (int jb = 0; jb < NQK; ++jb)
+          ptx::tma_load_4d_2sm(sQ + jb * 8192, &map_q, l_q_full, jb * 64, q0 + 64 * (int)rank, h, b);
+        for (int step = 0; step <= T; ++step) {
+          if (step < T) {
+            const int kv0 = step * 128;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KST; ++ks) {
+              const uint32_t stage = kc % Cfg::NKS, n = kc / Cfg::NKS;
+              ptx::mbar_wait(bar(bars.k_empty[stage]), (n & 1) ^ 1);
+              const int nb = (NQK - 2 * ks) >= 2 ? 2 : 1;
+              if (rank == 0) ptx::mbar_expect_tx(bar(bars.k_full[stage]), 2 * nb * 8192);
+              const uint32_t l_full = ptx::mapa(bar(bars.k_full[stage]), 0);
+              for (int bx = 0; bx < nb; ++bx)
+                ptx::tma_load_4d_2sm(sK + stage * 16384 + bx * 8192, &map_k, l_full, (2 * ks + bx) * 64,
+                                     kv0 + 64 * (int)rank, hk, b);
+              ++kc;
+            }
+          }
+          if (step >= 1) {
+            const int kv0 = (step - 1) * 128;
+#pragma unroll
+            for (int s = 0; s < Cfg::NSLICE; ++s) {
+              const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
+              ptx::mbar_wait(bar(bars.v_empty[stage]), (n & 1) ^ 1);
+              const int ns = Cfg::slice_n(s);
+              const int nb = ns / 128;  // 64-wide boxes this CTA loads
+              if (rank == 0) ptx::mbar_expect_tx(bar(bars.v_full[stage]), 2 * nb * 16384);
+              const uint32_t l_full = ptx::mapa(bar(bars.v_full[stage]), 0);
+              for (int bx = 0; bx < nb; ++bx)
+                ptx::tma_load_4d_2sm(sV + stage * 32768 + bx * 16384, &map_v, l_full,
+                                     256 * s + (ns / 2) * (int)rank + 64 * bx, kv0, hk, b);
+              ++vc;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    // =========================================== MMA issuer (leader CTA) ========================
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t fmt = BF16 ? 1u : 0u;
+      constexpr uint32_t idesc_qk = ptx::make_idesc(fmt, fmt, 0, 0, 128, 128);
+      uint32_t kc = 0, vc = 0, it = 0, g = 0, gp = 0;
+      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters, ++it) {
+        const int mt = item % p.n_mtiles;
+        const int T = num_kv_tiles(p, mt * 128);
+        ptx::mbar_wait(bar(bars.q_full), it & 1);
+        ptx::tc_fence_after();
+        for (int step = 0; step <= T; ++step) {
+          if (step < T) {
+            const uint32_t sbuf = g & 1;
+            const uint32_t d_tmem = tmem + Cfg::S_BASE + 64 * sbuf;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KST; ++ks) {
+              const uint32_t stage = kc % Cfg::NKS, n = kc / Cfg::NKS;
+              ptx::mbar_wait(bar(bars.k_full[stage]), n & 1);
+              ptx::tc_fence_after();
+              const int nb = (NQK - 2 * ks) >= 2 ? 2 : 1;
+              for (int bx = 0; bx < nb; ++bx) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const uint64_t ad = ptx::make_smem_desc_sw128(sQ + (2 * ks + bx) * 8192 + k4 * 32, 16, 1024);
+                  const uint64_t bd = ptx::make_smem_desc_sw128(sK + stage * 16384 + bx * 8192 + k4 * 32, 16, 1024);
+                  ptx::umma_f16_ss<CG>(d_tmem, ad, bd, idesc_qk, (ks | bx | k4) != 0 ? 1u : 0u);
+                }
+              }
+              ptx::umma_commit_mc<CG>(bar(bars.k_empty[stage]), 0x3);
+              ++kc;
+            }
+            ptx::umma_commit_mc<CG>(bar(bars.s_full[sbuf]), 0x3);
+            if (step == T - 1) ptx::umma_commit_mc<CG>(bar(bars.q_empty), 0x3);
+            ++g;
+          }
+          if (step >= 1) {
+            const uint32_t pbuf = gp & 1;
+            ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp >> 1) & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < Cfg::NSLICE; ++s) {
+              const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
+              ptx::mbar_wait(bar(bars.v_full[stage]), n & 1);
+              ptx::tc_fence_after();
+              const int ns = Cfg::slice_n(s);
+              const uint32_t idesc_pv = ptx::make_idesc(fmt, fmt, 0, 1, 128, ns);
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t ad = ptx::make_smem_desc_sw128(sP + pbuf * 16384 + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
+                const uint64_t bd = ptx::make_smem_desc_sw128(sV + stage * 32768 + kk * 2048, 16384, 1024);
+                ptx::umma_f16_ss<CG>(tmem + 128 * s, ad, bd, idesc_pv, (step > 1 || kk > 0) ? 1u : 0u);
+              }
+              ptx::umma_commit_mc<CG>(bar(bars.v_empty[stage]), 0x3);
+              ++vc;
+            }
+            ptx::umma_commit_mc<CG>(bar(bars.p_empty[pbuf]), 0x3);
+            ++gp;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================== softmax / correction / epilogue ================
+    const uint32_t t = threadIdx.x;          // 0..127 == TMEM lane
+    const uint32_t row = t & 63;             // row inside this CTA's 64
+    const uint32_t kh = t >> 6;              // which 64-key half of the KV tile / column half of O
+    const uint32_t lane_base = (warp * 32u) << 16;
+    const uint32_t l_p_full[2] = {ptx::mapa(bar(bars.p_full[0]), 0), ptx::mapa(bar(bars.p_full[1]), 0)};
+    const float NEG_INF = -INFINITY;
+    uint32_t g = 0;
+    for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
+      const int mt = item % p.n_mtiles;
+      const int bh = item / p.n_mtiles;
+      const int h = bh % p.heads_q, b = bh / p.heads_q;
+      const int q0 = mt * 128;
+      const int T = num_kv_tiles(p, q0);
+      const int gq = q0 + 64 * (int)rank + (int)row;  // global query row of this thread
+      const int causal_lim = gq + (p.seqlen_kv - p.seqlen_q);  // last visible key when causal
+      float m = NEG_INF, l = 0.f;
+
+      for (int i = 0; i < T; ++i, ++g) {
+        const uint32_t sbuf = g & 1;
+        ptx::mbar_wait(bar(bars.s_full[sbuf]), (g >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t sr[64];
+        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf, sr);
+        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32, sr + 32);
+        ptx::tmem_wait_ld();
+        float x[64];
+        const int key0 = i * 128 + 64 * (int)kh;
+        if (p.bias_kind == 0) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) x[j] = __uint_as_float(sr[j]) * p.scale_log2;
+        } else {
+          const int64_t boff = (int64_t)b * p.bias_stride[0] + (int64_t)h * p.bias_stride[1] +
+                               (int64_t)(gq < p.seqlen_q ? gq : 0) * p.bias_stride[2];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const int key = key0 + j;
+            float bv = 0.f;
+            if (key < p.seqlen_kv) {
+              if (p.bias_kind == 1) bv = reinterpret_cast<const float*>(p.bias)[boff + key];
+              else if (BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[boff + key]);
+              else bv = __half2float(reinterpret_cast<const __half*>(p.bias)[boff + key]);
+            }
+            x[j] = fmaf(__uint_as_float(sr[j]), p.scale_log2, bv * 1.4426950408889634f);
+          }
+        }
+        const bool tail = (i * 128 + 128 > p.seqlen_kv);
+        const bool diag = p.causal && (i * 128 + 127 > q0 + (p.seqlen_kv - p.seqlen_q));
+        if (tail || diag) {
+          const int lim = p.causal ? (causal_lim < p.seqlen_kv - 1 ? causal_lim : p.seqlen_kv - 1) : p.seqlen_kv - 1;
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (key0 + j > lim) x[j] = NEG_INF;
+        }
+        float tmax = x[0];
+#pragma unroll
+        for (int j = 1; j < 64; ++j) tmax = fmaxf(tmax, x[j]);
+        xch[sbuf][t] = tmax;
+        ptx::named_bar_sync(1, 128);
+        tmax = fmaxf(tmax, xch[sbuf][t ^ 64]);
+        // lazy rescale: keep the stale max while the true max is < 8 (log2 units) above it
+        // (/root/reference/csrc/cuffpa/native/prefill.cuh:719-738, common.cuh:14-18)
+        const float m_new = fmaxf(m, tmax);
+        const bool upd = (m_new - m) > 8.0f;  // also true for -inf -> finite; false for -inf -> -inf
+        const float m_use = upd ? m_new : m;
+        const bool need_rescale = upd && (m != NEG_INF);
+        const float m_safe = (m_use == NEG_INF) ? 0.f : m_use;
+        float lsum = 0.f;
+        uint32_t pk[32];
+        if constexpr (DROPOUT) {
+          // dropout: keep iff u > p; row sum uses the un-dropped probabilities
+          // (/root/reference/csrc/cuffpa/native/prefill.cuh:506-546)
+          const float inv_keep = 1.f / (1.f - p.dropout_p);
+          const uint64_t ebase = p.philox_offset +
+              ((uint64_t)((int64_t)b * p.heads_q + h) * (uint64_t)p.seqlen_q + (uint64_t)(gq < p.seqlen_q ? gq : 0)) * (uint64_t)p.seqlen_kv +
+              (uint64_t)key0;
+#pragma unroll
+          for (int j4 = 0; j4 < 64; j4 += 4) {
+            // 4 consecutive element offsets may straddle two Philox quads when ebase % 4 != 0
+            float pv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float e = ptx::ex2_approx(x[j4 + u] - m_safe);
+              lsum += e;
+              const uint64_t eo = ebase + (uint64_t)(j4 + u);
+              const uint4 r4 = philox4x32_10(p.philox_seed, eo >> 2);
+              const uint32_t sel = (uint32_t)(eo & 3);
+              const uint32_t rv = sel == 0 ? r4.x : sel == 1 ? r4.y : sel == 2 ? r4.z : r4.w;
+              const float uni = ((float)rv + 1.0f) * 2.3283064365386963e-10f;
+              pv[u] = (uni > p.dropout_p) ? e * inv_keep : 0.f;
+            }
+            pk[(j4 >> 1)] = BF16 ? ptx::pack_bf16x2(pv[0], pv[1]) : ptx::pack_f16x2(pv[0], pv[1]);
+            pk[(j4 >> 1) + 1] = BF16 ? ptx::pack_bf16x2(pv[2], pv[3]) : ptx::pack_f16x2(pv[2], pv[3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; j += 2) {
+            const float e0 = ptx::ex2_approx(x[j] - m_safe);
+            const float e1 = ptx::ex2_approx(x[j + 1] - m_safe);
+            lsum += e0 + e1;
+            pk[j >> 1] = BF16 ? ptx::pack_bf16x2(e0, e1) : ptx::pack_f16x2(e0, e1);
+          }
+        }
+        float factor = 1.f;
+        if (need_rescale) factor = ptx::ex2_approx(m - m_use);
+        l = l * factor + lsum;
+        m = m_use;
+
+        // P buffer free? (PV of tile g-2 retired)
+        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((g >> 1) & 1) ^ 1);
+        {
+          const uint32_t prow = sP + sbuf * 16384 + kh * 8192 + row * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t addr = prow + ((c ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
+                         "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                         : "memory");
+          }
+        }
+        if (__any_sync(0xffffffffu, need_rescale)) {
+          // O may only be touched once PV of tile g-1 has retired
+          ptx::mbar_wait(bar(bars.p_empty[(g - 1) & 1]), ((g - 1) >> 1) & 1);
+          ptx::tc_fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < Cfg::O_COLS; c0 += 32) {
+            uint32_t orr[32];
+            ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * factor);
+            ptx::tmem_st_x32(tmem + lane_base + c0, orr);
+          }
+          ptx::tmem_wait_st();
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(l_p_full[sbuf]);
+      }
+
+      // ---------------- epilogue: O / l -> global, LSE ----------------
+      {
+        const uint32_t gl = g - 1;
+        ptx::mbar_wait(bar(bars.p_empty[gl & 1]), (gl >> 1) & 1);
+        ptx::tc_fence_after();
+        xl[t] = l;
+        ptx::named_bar_sync(1, 128);
+        const float l_tot = l + xl[t ^ 64];
+        const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        const bool row_ok = gq < p.seqlen_q;
+        uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
+                        2 * ((int64_t)b * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)gq * p.o_stride[2]);
+#pragma unroll
+        for (int s = 0; s < Cfg::NSLICE; ++s) {
+          const int ns = Cfg::slice_n(s);
+#pragma unroll 1
+          for (int c0 = 0; c0 < ns / 2; c0 += 32) {
+            uint32_t orr[32];
+            ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
+            ptx::tmem_wait_ld();
+            const int d0 = 256 * s + (ns / 2) * (int)kh + c0;
+            if (row_ok) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                const int d = d0 + 8 * v;
+                if (d < p.head_dim) {
+                  uint32_t w[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float a = __uint_as_float(orr[8 * v + 2 * u]) * inv;
+                    const float c = __uint_as_float(orr[8 * v + 2 * u + 1]) * inv;
+                    w[u] = BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
+                  }
+                  *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+              }
+            }
+          }
+        }
+        if (p.lse != nullptr && kh == 0 && row_ok) {
+          // natural-log LSE; rows without any visible key: O = 0, LSE = -inf
+          const float lse = (l_tot > 0.f) ? (m + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
+          p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
+        }
+        ptx::tc_fence_before();
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 4) ptx::tmem_dealloc<CG>(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------------
+template <int NQK, bool BF16, bool DROPOUT>
+static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                          const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
+  using Cfg = FwdCfg<NQK>;
+  auto kern = ffpa_fwd_kernel<NQK, BF16, DROPOUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN);
+    if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "forward launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return FFPA_OK;
+}
+
+template <bool BF16, bool DROPOUT>
+static int dispatch_nqk(int nqk, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                        const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
+  switch (nqk) {
+    case 1: return launch_variant<1, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
+    case 2: return launch_variant<2, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
+    case 3: return launch_variant<3, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
+    case 4: return launch_variant<4, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
+    case 5: return launch_variant<5, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
+    case 6: return launch_variant<6, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
+    case 7: return launch_variant<7, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
+    case 8: return launch_variant<8, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
+    default: return set_error(FFPA_ERR_UNSUPPORTED, "head_dim > 512 not supported by this kernel");
+  }
+}
+
+static bool make_map(CUtensorMap* m, const void* base, const int64_t* stride, int B, int H, int N,
+                     int D, uint32_t box_d, uint32_t box_n) {
+  uint64_t dims[4] = {(uint64_t)D, (uint64_t)N, (uint64_t)H, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)stride[2] * 2, (uint64_t)stride[1] * 2, (uint64_t)stride[0] * 2};
+  // size-1 dims may carry arbitrary (even 0) strides; TMA wants multiples of 16 and > 0
+  for (int i = 0; i < 3; ++i)
+    if (dims[i + 1] == 1) str[i] = (uint64_t)D * 2 * (i >= 1 ? (uint64_t)N : 1) * (i >= 2 ? (uint64_t)H : 1);
+  uint32_t box[4] = {box_d, box_n, 1, 1};
+  return tmap::encode_sw128(m, const_cast<void*>(base), 2, 4, dims, str, box);
+}
+
+int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
+  const int D = a.head_dim;
+  const int nqk = (D + 63) / 64;
+  CUtensorMap mq, mk, mv;
+  if (!make_map(&mq, a.q, a.q_stride, a.batch, a.heads_q, a.seqlen_q, D, 64, 64) ||
+      !make_map(&mk, a.k, a.k_stride, a.batch, a.heads_kv, a.seqlen_kv, D, 64, 64) ||
+      !make_map(&mv, a.v, a.v_stride, a.batch, a.heads_kv, a.seqlen_kv, D, 64, 128))
+    return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed (strides must be multiples of 8 elements, base 16-byte aligned)");
+
+  FwdKernelParams kp{};
+  kp.o = a.o;
+  kp.lse = a.lse;
+  kp.bias = a.bias;
+  for (int i = 0; i < 3; ++i) kp.o_stride[i] = a.o_stride[i];
+  for (int i = 0; i < 4; ++i) kp.bias_stride[i] = a.bias_stride[i];
+  kp.batch = a.batch; kp.heads_q = a.heads_q; kp.heads_kv = a.heads_kv;
+  kp.seqlen_q = a.seqlen_q; kp.seqlen_kv = a.seqlen_kv; kp.head_dim = D;
+  kp.causal = a.causal; kp.bias_kind = a.bias_kind;
+  kp.scale_log2 = a.softmax_scale * 1.4426950408889634f;
+  kp.dropout_p = a.dropout_p;
+  kp.philox_seed = a.philox_seed; kp.philox_offset = a.philox_offset;
+  kp.n_mtiles = (a.seqlen_q + 127) / 128;
+  kp.n_items = kp.n_mtiles * a.batch * a.heads_q;
+
+  int nsm = sm_count();
+  int nclusters = nsm / 2;
+  if (nclusters > kp.n_items) nclusters = kp.n_items;
+  const bool drop = a.dropout_p > 0.f;
+  if (a.dtype == FFPA_DTYPE_BF16)
+    return drop ? dispatch_nqk<true, true>(nqk, mq, mk, mv, kp, nclusters, stream)
+                : dispatch_nqk<true, false>(nqk, mq, mk, mv, kp, nclusters, stream);
+  return drop ? dispatch_nqk<false, true>(nqk, mq, mk, mv, kp, nclusters, stream)
+              : dispatch_nqk<false, false>(nqk, mq, mk, mv, kp, nclusters, stream);
+}
+
+}  // namespace ffpa

@@ -1,0 +1,33 @@
+// Internal declarations shared by the C-ABI translation unit and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/ffpa_b200.h"
+
+namespace ffpa {
+
+// kernel-side view of ffpa_fwd_params (tensor maps carry Q/K/V)
+struct FwdKernelParams {
+  void* o;
+  float* lse;
+  const void* bias;
+  int64_t o_stride[3];     // (b, h, n) in elements
+  int64_t bias_stride[4];  // (b, h, q, k) in elements
+  int batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
+  int causal, bias_kind;
+  float scale_log2;  // softmax_scale * log2(e)
+  float dropout_p;
+  uint64_t philox_seed, philox_offset;
+  int n_mtiles, n_items;
+};
+
+int set_error(int code, const char* fmt, ...);
+void count_launch();
+int sm_count();
+
+int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream);
+int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream);
+uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv,
+                             int head_dim);
+
+}  // namespace ffpa

@@ -1,0 +1,125 @@
+/* ffpa_b200.h -- C ABI of the B200-native (sm_100a) Split-D attention engine.
+ *
+ * This is the drop-in boundary for the reference's native backend. The reference binds its CUDA
+ * backend through a pybind11 module `ffpa_attn._C`
+ *   (/root/reference/csrc/cuffpa/ffpa_api.cc:86-96  ffpa_attn_forward,
+ *    /root/reference/csrc/cuffpa/ffpa_api.cc:242-246 ffpa_attn_backward (a stub that throws),
+ *    /root/reference/csrc/cuffpa/backend.h:6-27      set/get_cuda_backend_impl)
+ * whose arguments are torch tensors. The entry points below carry exactly the same information
+ * as plain device pointers + sizes + strides, so they can be bound from pybind/torch (see
+ * INTEGRATION.md), ctypes (ffpa-attn_b200/ffpa_attn/cuda/_C.py) or any other FFI.
+ *
+ * Conventions (identical to the reference contract):
+ *   Q  [B, Hq,  Nq,  D]   K,V [B, Hkv, Nkv, D]   O like Q   LSE fp32 [B, Hq, Nq] natural log
+ *   dtype fp16 or bf16, last dim contiguous (stride 1), other strides in ELEMENTS and
+ *   multiples of 8 (16 bytes, a TMA requirement); Hq % Hkv == 0 (GQA: kv_head = q_head / group);
+ *   causal is bottom-right aligned (key k visible to row r iff k <= r + Nkv - Nq), needs Nkv>=Nq;
+ *   attn bias is additive, applied after scaling, broadcast through zero strides, fp32 or the
+ *   Q dtype, mutually exclusive with causal; dropout uses Philox-4x32-10 keyed by (seed, offset)
+ *   with element index ((b*Hq+h)*Nq+q)*Nkv+k, keep iff u > p, scale 1/(1-p).
+ *   All work is enqueued on `stream` (a cudaStream_t); no host synchronisation.
+ *
+ * Every function returns 0 on success, a negative FFPA_ERR_* code otherwise;
+ * ffpa_b200_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef FFPA_B200_H_
+#define FFPA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFPA_B200_ABI_VERSION 1
+
+enum {
+  FFPA_OK = 0,
+  FFPA_ERR_INVALID_ARGUMENT = -1, /* shape / dtype / stride contract violated (TORCH_CHECK class) */
+  FFPA_ERR_UNSUPPORTED = -2,      /* valid request this build does not implement               */
+  FFPA_ERR_CUDA = -3,             /* CUDA runtime / driver error                                */
+  FFPA_ERR_NO_DEVICE = -4         /* device is not sm_100                                       */
+};
+
+enum { FFPA_DTYPE_F16 = 0, FFPA_DTYPE_BF16 = 1 };
+enum { FFPA_BIAS_NONE = 0, FFPA_BIAS_F32 = 1, FFPA_BIAS_QDTYPE = 2 };
+
+/* mirrors ffpa::CudaBackendImpl (/root/reference/csrc/cuffpa/backend.h:6-14); advisory here:
+ * 0..4 -> the sm_100a bf16/fp16 kernel, 5 -> FP8 kernel, 6 -> unsupported. */
+enum {
+  FFPA_IMPL_AUTO = 0, FFPA_IMPL_NATIVE = 1, FFPA_IMPL_TMA = 2, FFPA_IMPL_CUTE = 3,
+  FFPA_IMPL_CUTE_TMA = 4, FFPA_IMPL_CUTE_TMA_FP8 = 5, FFPA_IMPL_CUTE_TMA_FP4 = 6
+};
+
+typedef struct ffpa_fwd_params {
+  /* tensors (device pointers) */
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  float* lse;        /* [B, Hq, Nq] contiguous fp32; may be NULL (not written) */
+  const void* bias;  /* NULL when bias_kind == FFPA_BIAS_NONE */
+  /* element strides, order (b, h, n, d); d-stride must be 1 */
+  int64_t q_stride[4];
+  int64_t k_stride[4];
+  int64_t v_stride[4];
+  int64_t o_stride[4];
+  int64_t bias_stride[4]; /* (b, h, q, k); 0 on broadcast dims; k-stride must be 1 */
+  /* sizes */
+  int32_t batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
+  int32_t dtype;     /* FFPA_DTYPE_* */
+  int32_t bias_kind; /* FFPA_BIAS_* */
+  int32_t causal;    /* 0 / 1 */
+  int32_t fp8;       /* 0: fp16/bf16 MMA; 1: per-tile e4m3 quantised MMA (FFPA_IMPL_CUTE_TMA_FP8) */
+  float softmax_scale;
+  float dropout_p;
+  uint64_t philox_seed;
+  uint64_t philox_offset;
+} ffpa_fwd_params;
+
+typedef struct ffpa_bwd_params {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* o;
+  const float* lse;
+  const void* d_o;
+  void* dq;
+  void* dk;
+  void* dv;
+  int64_t q_stride[4], k_stride[4], v_stride[4], o_stride[4], do_stride[4];
+  int64_t dq_stride[4], dk_stride[4], dv_stride[4];
+  int32_t batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
+  int32_t dtype;
+  int32_t causal;
+  float softmax_scale;
+  /* scratch: fp32 workspace of ffpa_b200_bwd_workspace_bytes() bytes (device) */
+  void* workspace;
+  uint64_t workspace_bytes;
+} ffpa_bwd_params;
+
+/* replaces ffpa_attn_forward (/root/reference/csrc/cuffpa/ffpa_api.cc:86-239) */
+int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream);
+
+/* replaces ffpa_attn_backward (/root/reference/csrc/cuffpa/ffpa_api.cc:242-263, a thrower there) */
+int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream);
+uint64_t ffpa_b200_bwd_workspace_bytes(int32_t batch, int32_t heads_q, int32_t heads_kv,
+                                       int32_t seqlen_q, int32_t seqlen_kv, int32_t head_dim);
+
+/* replaces set_cuda_backend_impl / get_cuda_backend_impl (ffpa_api.cc:272-282, backend.h:16-25) */
+int ffpa_b200_set_backend_impl(int32_t impl);
+int32_t ffpa_b200_get_backend_impl(void);
+
+/* capability flags = the module attributes of ffpa_api.cc:283-305 */
+int32_t ffpa_b200_fwd_available(void);
+int32_t ffpa_b200_bwd_available(void);
+int32_t ffpa_b200_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t ffpa_b200_launch_count(void);
+
+const char* ffpa_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFPA_B200_H_ */
