@@ -1,0 +1,208 @@
+"""CPU tests for the boundary: the C-ABI library loads and exports every symbol declared in
+include/ffpa_b200.h, the ctypes structs match the C layout, and the host-side mirror of the
+reference API validates inputs with the reference's error classes. No kernel is launched."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ffpa_b200.h")
+LIB = os.path.join(ROOT, "ffpa-attn_b200", "ffpa_attn", "libffpa_b200.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+  if not os.path.exists(LIB):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+
+    ge.build()
+  return ctypes.CDLL(LIB)
+
+
+def _declared_symbols():
+  src = open(HEADER).read()
+  return sorted(set(re.findall(r"\b(ffpa_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+  syms = _declared_symbols()
+  for s in ("ffpa_b200_fwd", "ffpa_b200_bwd", "ffpa_b200_set_backend_impl", "ffpa_b200_get_backend_impl",
+            "ffpa_b200_last_error", "ffpa_b200_launch_count", "ffpa_b200_bwd_workspace_bytes"):
+    assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+  for s in _declared_symbols():
+    assert hasattr(lib, s), f"libffpa_b200.so does not export {s}"
+
+
+def test_abi_version_and_flags(lib):
+  lib.ffpa_b200_abi_version.restype = ctypes.c_int32
+  assert lib.ffpa_b200_abi_version() == 1
+  assert lib.ffpa_b200_fwd_available() == 1
+
+
+def test_ctypes_struct_layout_matches_c():
+  import ffpa_attn._C as C
+
+  prog = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "ffpa_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ffpa_fwd_params), offsetof(ffpa_fwd_params, bias_stride),
+         offsetof(ffpa_fwd_params, batch), offsetof(ffpa_fwd_params, softmax_scale),
+         offsetof(ffpa_fwd_params, philox_seed), offsetof(ffpa_fwd_params, philox_offset));
+  printf("%zu %zu %zu %zu\n", sizeof(ffpa_bwd_params), offsetof(ffpa_bwd_params, batch),
+         offsetof(ffpa_bwd_params, softmax_scale), offsetof(ffpa_bwd_params, workspace));
+  return 0;
+}
+"""
+  with tempfile.TemporaryDirectory() as d:
+    src = os.path.join(d, "t.c")
+    open(src, "w").write(prog)
+    exe = os.path.join(d, "t")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+    out = subprocess.check_output([exe]).decode().split()
+  F, B = C._FwdParams, C._BwdParams
+  want = [ctypes.sizeof(F), F.bias_stride.offset, F.batch.offset, F.softmax_scale.offset,
+          F.philox_seed.offset, F.philox_offset.offset,
+          ctypes.sizeof(B), B.batch.offset, B.softmax_scale.offset, B.workspace.offset]
+  assert [int(x) for x in out] == want
+
+
+def test_backend_hint_roundtrip(lib):
+  import ffpa_attn
+
+  ffpa_attn.set_cuda_backend_impl(ffpa_attn.CudaBackendImpl.TMA)
+  assert ffpa_attn.get_cuda_backend_impl() == ffpa_attn.CudaBackendImpl.TMA
+  ffpa_attn.set_cuda_backend_impl(ffpa_attn.CudaBackendImpl.AUTO)
+  with pytest.raises(RuntimeError):
+    ffpa_attn._C.set_cuda_backend_impl(99)
+
+
+def test_c_abi_rejects_bad_arguments_without_a_gpu(lib):
+  """Argument validation happens before any CUDA work except the device probe; on a box with no
+  GPU every call must fail loudly (no silent CPU path)."""
+  import ffpa_attn._C as C
+
+  p = C._FwdParams()
+  rc = C._lib.ffpa_b200_fwd(ctypes.byref(p), None)
+  assert rc < 0
+  assert len(C._lib.ffpa_b200_last_error()) > 0
+  assert C._lib.ffpa_b200_fwd(None, None) == -1
+
+
+# ---- host-side API semantics (reference: tests/test_ffpa_fwd.py:162-177, 1146-1152, 1199-1215) ----
+def _qkv(B=1, Hq=2, Hkv=2, Nq=16, Nkv=16, D=64, dtype=torch.bfloat16):
+  q = torch.randn(B, Hq, Nq, D, dtype=dtype)
+  k = torch.randn(B, Hkv, Nkv, D, dtype=dtype)
+  v = torch.randn(B, Hkv, Nkv, D, dtype=dtype)
+  return q, k, v
+
+
+def test_unknown_kwarg_is_type_error():
+  from ffpa_attn import ffpa_attn_func
+
+  q, k, v = _qkv()
+  with pytest.raises(TypeError, match="unexpected keyword"):
+    ffpa_attn_func(q, k, v, not_a_kwarg=1)
+
+
+def test_fp32_inputs_are_type_error():
+  from ffpa_attn import ffpa_attn_func
+
+  q, k, v = _qkv(dtype=torch.float32)
+  with pytest.raises(TypeError, match="fp16/bf16"):
+    ffpa_attn_func(q, k, v)
+
+
+def test_gqa_needs_opt_in_and_divisibility():
+  from ffpa_attn import ffpa_attn_func
+
+  q, k, v = _qkv(Hq=4, Hkv=2)
+  with pytest.raises(ValueError, match="enable_gqa"):
+    ffpa_attn_func(q, k, v)
+  q, k, v = _qkv(Hq=3, Hkv=2)
+  with pytest.raises(ValueError, match="integer multiple"):
+    ffpa_attn_func(q, k, v, enable_gqa=True)
+
+
+def test_causal_requires_nkv_ge_nq_and_excludes_mask():
+  from ffpa_attn import ffpa_attn_func
+
+  q, k, v = _qkv(Nq=32, Nkv=16)
+  with pytest.raises(ValueError, match="Nkv >= Nq"):
+    ffpa_attn_func(q, k, v, is_causal=True)
+  q, k, v = _qkv()
+  with pytest.raises(RuntimeError, match="attn_mask"):
+    ffpa_attn_func(q, k, v, attn_mask=torch.ones(16, 16, dtype=torch.bool), is_causal=True)
+
+
+def test_dropout_range_and_shapes():
+  from ffpa_attn import ffpa_attn_func
+
+  q, k, v = _qkv()
+  with pytest.raises(ValueError):
+    ffpa_attn_func(q, k, v, dropout_p=1.0)
+  with pytest.raises(ValueError):
+    ffpa_attn_func(q, k, v, dropout_p=-0.1)
+  with pytest.raises(ValueError, match="4-D"):
+    ffpa_attn_func(q[0], k[0], v[0])
+
+
+def test_cpu_tensors_fail_loudly_no_fallback():
+  from ffpa_attn import ffpa_attn_func
+
+  q, k, v = _qkv()
+  with pytest.raises(RuntimeError, match="no CPU"):
+    ffpa_attn_func(q, k, v)
+
+
+def test_backend_kwarg_accepts_only_cuda():
+  from ffpa_attn import CUDABackend, FFPAAttnMeta
+
+  m = FFPAAttnMeta.from_kwargs(backend="cuda")
+  assert isinstance(m.forward_meta, CUDABackend)
+  m = FFPAAttnMeta.from_kwargs(forward_backend=CUDABackend(enable_fp8=True))
+  assert m.forward_meta.impl_hint.name == "CUTE_TMA_FP8"
+  for name in ("triton", "cutedsl", "sdpa"):
+    with pytest.raises(NotImplementedError):
+      FFPAAttnMeta.from_kwargs(backend=name)
+  with pytest.raises(ValueError):
+    CUDABackend(acc="f16")
+  with pytest.raises(TypeError):
+    FFPAAttnMeta.from_kwargs(backend=3)
+
+
+def test_mask_normalisation_matches_reference_rules():
+  from ffpa_attn import FFPAAttnMeta
+
+  meta = FFPAAttnMeta()
+  q, k, _ = _qkv(B=2, Nq=8, Nkv=12)
+  m2 = torch.rand(8, 12) > 0.5
+  b = meta.normalize_attn_mask(q, k, m2)
+  assert b.shape == (1, 1, 8, 12) and b.dtype == q.dtype
+  assert set(b.unique().tolist()) <= {0.0, float("-inf")}
+  m3 = torch.randn(2, 8, 12)
+  assert meta.normalize_attn_mask(q, k, m3).shape == (2, 1, 8, 12)
+  with pytest.raises(ValueError, match="broadcastable"):
+    meta.normalize_attn_mask(q, k, torch.zeros(3, 1, 8, 12))
+  with pytest.raises(TypeError, match="dtype"):
+    meta.normalize_attn_mask(q, k, torch.zeros(8, 12, dtype=torch.float64))
+
+
+def test_fake_op_registered_for_compile():
+  import ffpa_attn  # noqa: F401
+
+  q = torch.empty(1, 2, 16, 64, dtype=torch.bfloat16, device="meta")
+  o, lse = torch.ops.ffpa_attn._fwd_cuda(q, q, q, q.new_empty(0), 0, 1, 0, 0.125, 0.0, 0, 0, True, False,
+                                         0, 0, 0, 0, 0, False, 256, False, 256)
+  assert o.shape == q.shape and lse.shape == (1, 2, 16) and lse.dtype == torch.float32
