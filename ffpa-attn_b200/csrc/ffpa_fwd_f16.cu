@@ -1,0 +1,6 @@
+// fp16 instantiations of the forward kernel family
+#include "ffpa_fwd_sm100.cuh"
+namespace ffpa {
+template int dispatch_fwd_dtype<false>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                                       const FwdKernelParams&, int, cudaStream_t);
+}

@@ -1,0 +1,62 @@
+// Host launcher of the forward: tensor-map construction (passed as __grid_constant__ kernel
+// parameters -- no per-launch cudaMalloc/cudaMemcpy as in
+// /root/reference/csrc/cuffpa/native/launch.cuh:503-509), persistent grid sizing, mode selection.
+#include "ffpa_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace ffpa {
+
+template <bool BF16>
+int dispatch_fwd_dtype(int nqk, int mode, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                       const FwdKernelParams& kp, int nclusters, cudaStream_t stream);
+extern template int dispatch_fwd_dtype<true>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                                             const FwdKernelParams&, int, cudaStream_t);
+extern template int dispatch_fwd_dtype<false>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                                              const FwdKernelParams&, int, cudaStream_t);
+
+static bool make_map(CUtensorMap* m, const void* base, const int64_t* stride, int B, int H, int N,
+                     int D, uint32_t box_d, uint32_t box_n) {
+  uint64_t dims[4] = {(uint64_t)D, (uint64_t)N, (uint64_t)H, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)stride[2] * 2, (uint64_t)stride[1] * 2, (uint64_t)stride[0] * 2};
+  // size-1 dims may carry arbitrary strides; give TMA the packed one (multiple of 16 bytes)
+  const uint64_t packed[3] = {(uint64_t)D * 2, (uint64_t)D * 2 * N, (uint64_t)D * 2 * N * H};
+  for (int i = 0; i < 3; ++i)
+    if (dims[i + 1] == 1) str[i] = packed[i];
+  uint32_t box[4] = {box_d, box_n, 1, 1};
+  return tmap::encode_sw128(m, const_cast<void*>(base), 2, 4, dims, str, box);
+}
+
+int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
+  const int D = a.head_dim;
+  const int nqk = (D + 63) / 64;
+  CUtensorMap mq, mk, mv;
+  if (!make_map(&mq, a.q, a.q_stride, a.batch, a.heads_q, a.seqlen_q, D, 64, 64) ||
+      !make_map(&mk, a.k, a.k_stride, a.batch, a.heads_kv, a.seqlen_kv, D, 64, 64) ||
+      !make_map(&mv, a.v, a.v_stride, a.batch, a.heads_kv, a.seqlen_kv, D, 64, 128))
+    return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed (strides must be multiples of 8 elements, base 16-byte aligned)");
+
+  FwdKernelParams kp{};
+  kp.o = a.o;
+  kp.lse = a.lse;
+  kp.bias = a.bias;
+  for (int i = 0; i < 3; ++i) kp.o_stride[i] = a.o_stride[i];
+  for (int i = 0; i < 4; ++i) kp.bias_stride[i] = a.bias_stride[i];
+  kp.batch = a.batch; kp.heads_q = a.heads_q; kp.heads_kv = a.heads_kv;
+  kp.seqlen_q = a.seqlen_q; kp.seqlen_kv = a.seqlen_kv; kp.head_dim = D;
+  kp.causal = a.causal; kp.bias_kind = a.bias_kind;
+  kp.scale_log2 = a.softmax_scale * 1.4426950408889634f;
+  kp.dropout_p = a.dropout_p;
+  kp.philox_seed = a.philox_seed; kp.philox_offset = a.philox_offset;
+  kp.n_mtiles = (a.seqlen_q + 127) / 128;
+  kp.n_items = kp.n_mtiles * a.batch * a.heads_q;
+
+  int nclusters = sm_count() / 2;
+  if (nclusters > kp.n_items) nclusters = kp.n_items;
+  int mode = 0;  // fast
+  if (a.dropout_p > 0.f) mode = 2;
+  else if (a.bias_kind != FFPA_BIAS_NONE || !(a.softmax_scale > 0.f)) mode = 1;
+  if (a.dtype == FFPA_DTYPE_BF16) return dispatch_fwd_dtype<true>(nqk, mode, mq, mk, mv, kp, nclusters, stream);
+  return dispatch_fwd_dtype<false>(nqk, mode, mq, mk, mv, kp, nclusters, stream);
+}
+
+}  // namespace ffpa

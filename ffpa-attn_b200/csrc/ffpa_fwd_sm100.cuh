@@ -2,10 +2,10 @@
 // warp-specialised persistent kernel.
 //
 // Replaces the reference's forward kernels behind the same boundary:
-//   /root/reference/csrc/cuffpa/launch.cuh:61-606            (launcher contract / checks)
+//   /root/reference/csrc/cuffpa/launch.cuh:61-606               (launcher contract / checks)
 //   /root/reference/csrc/cuffpa/native/sm_80/split_d.cuh:85-777 (Split-D algorithm)
-//   /root/reference/csrc/cuffpa/native/prefill.cuh:252-1172  (numerics: mask, online softmax with
-//                                                              lazy rescale, LSE)
+//   /root/reference/csrc/cuffpa/native/prefill.cuh:252-1172     (numerics: mask, online softmax
+//                                                                 with lazy rescale, dropout, LSE)
 // Design:
 //   * a 2-CTA cluster owns 128 query rows of one (batch, head); CTA r owns rows [64r, 64r+64).
 //   * S = Q K^T  : tcgen05.mma cta_group::2, M=128 N=128, K = head_dim split into 64-wide boxes
@@ -13,8 +13,10 @@
 //   * O += P V   : tcgen05.mma cta_group::2, M=128 N=256 (head-dim slices), K = 128 keys;
 //                  each CTA stages its P rows and its 128 head-dim columns of V (MN-major).
 //   * accumulators are "lane folded": TMEM lane l of CTA r holds row 64r + l%64, column half l/64.
-//   * warps 0-3 softmax/correction/epilogue, warp 4 MMA issue (leader CTA) + TMEM alloc,
-//     warp 5 TMA producer. mbarrier pipelines: K ring, V ring, S (2), P (2).
+//   * warps 0-7 softmax/correction/epilogue (two warpgroups, each owning half of the S columns),
+//     warp 8 MMA issue (leader CTA) + TMEM alloc, warp 9 TMA producer.
+//     mbarrier pipelines: K ring, V ring, S (2 stages), P (2 stages).
+#pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cmath>
@@ -23,8 +25,16 @@
 
 namespace ffpa {
 
-constexpr int kThreads = 192;
+constexpr int kSoftmaxWarps = 8;
+constexpr int kMmaWarp = 8;
+constexpr int kTmaWarp = 9;
+constexpr int kThreads = 320;
 constexpr int kSmemLimit = 232448;
+
+// softmax flavour
+constexpr int kModeFast = 0;     // no bias, scale > 0, no dropout
+constexpr int kModeGeneral = 1;  // additive bias and/or scale <= 0
+constexpr int kModeDropout = 2;  // general + Philox dropout
 
 template <int NQK>
 struct FwdCfg {
@@ -37,10 +47,10 @@ struct FwdCfg {
   static constexpr int Q_BYTES = NQK * 8192;
   static constexpr int P_BYTES = 2 * 16384;
   static constexpr int NVS = (HD > 256) ? 2 : 3;          // 32 KB V stages
-  static constexpr int kBudget = kSmemLimit - 2048 - 1024;  // static smem + alignment slack
+  static constexpr int kBudget = kSmemLimit - 3072;  // static smem (barriers + exchange), 1 KB aligned
   static constexpr int kNksRaw = (kBudget - Q_BYTES - P_BYTES - NVS * 32768) / 16384;
   static constexpr int NKS = kNksRaw > 8 ? 8 : kNksRaw;   // 16 KB K stages
-  static constexpr int SMEM_DYN = Q_BYTES + P_BYTES + NKS * 16384 + NVS * 32768 + 1024;
+  static constexpr int SMEM_DYN = Q_BYTES + P_BYTES + NKS * 16384 + NVS * 32768;
   static_assert(NKS >= 2, "not enough shared memory for the K ring");
   static_assert(O_COLS <= 256, "O does not fit TMEM next to S");
   __host__ __device__ static constexpr int slice_n(int s) { return (DVP - 256 * s) >= 256 ? 256 : 128; }
@@ -81,7 +91,28 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr) {
   return make_uint4(c0, c1, c2, c3);
 }
 
-template <int NQK, bool BF16, bool DROPOUT>
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)),
+        "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+template <int NQK, bool BF16, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const FwdKernelParams p) {
@@ -89,11 +120,11 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   constexpr int CG = 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ Barriers bars;
-  __shared__ float xch[2][128];
-  __shared__ float xl[128];
+  __shared__ float xch[2][4][64];  // per-tile row-max exchange: [S stage][kh*2+ch][row]
   __shared__ uint32_t tmem_slot;
 
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();  // SWIZZLE_128B tiles need 1 KB alignment
   const uint32_t sQ = smem_base;
   const uint32_t sP = sQ + Cfg::Q_BYTES;
   const uint32_t sK = sP + Cfg::P_BYTES;
@@ -113,17 +144,17 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     for (int i = 0; i < 3; ++i) { ptx::mbar_init(bar(bars.v_full[i]), 1); ptx::mbar_init(bar(bars.v_empty[i]), 1); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar(bars.s_full[i]), 1);
-      ptx::mbar_init(bar(bars.p_full[i]), 8);  // 4 softmax warps x 2 CTAs
+      ptx::mbar_init(bar(bars.p_full[i]), 2 * kSoftmaxWarps);  // softmax warps of both CTAs
       ptx::mbar_init(bar(bars.p_empty[i]), 1);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 5 && ptx::elect_one()) {
+  if (warp == kTmaWarp && ptx::elect_one()) {
     ptx::prefetch_tmap(&map_q);
     ptx::prefetch_tmap(&map_k);
     ptx::prefetch_tmap(&map_v);
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     ptx::tmem_alloc<CG>(ptx::smem_u32(&tmem_slot), 512);
     ptx::tmem_relinquish<CG>();
   }
@@ -134,7 +165,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   const int group = p.heads_q / p.heads_kv;
 
-  if (warp == 5) {
+  if (warp == kTmaWarp) {
     // =========================================== TMA producer ===================================
     if (ptx::elect_one()) {
       uint32_t kc = 0, vc = 0, it = 0;
@@ -187,7 +218,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // =========================================== MMA issuer (leader CTA) ========================
     if (rank == 0 && ptx::elect_one()) {
       constexpr uint32_t fmt = BF16 ? 1u : 0u;
@@ -252,12 +283,20 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     __syncwarp();
   } else {
     // =========================================== softmax / correction / epilogue ================
-    const uint32_t t = threadIdx.x;          // 0..127 == TMEM lane
-    const uint32_t row = t & 63;             // row inside this CTA's 64
-    const uint32_t kh = t >> 6;              // which 64-key half of the KV tile / column half of O
-    const uint32_t lane_base = (warp * 32u) << 16;
-    const uint32_t l_p_full[2] = {ptx::mapa(bar(bars.p_full[0]), 0), ptx::mapa(bar(bars.p_full[1]), 0)};
+    // 256 threads: TMEM lane = t % 128; warpgroup ch = t / 128 owns S columns [32ch, 32ch+32).
+    const uint32_t t = threadIdx.x;
+    const uint32_t lane128 = t & 127;
+    const uint32_t row = lane128 & 63;        // row inside this CTA's 64
+    const uint32_t kh = lane128 >> 6;         // 64-key half of the KV tile / column half of O
+    const uint32_t ch = t >> 7;               // column half inside the S stage
+    const uint32_t slot = kh * 2 + ch;
+    const uint32_t rgrp = warp & 1;           // warps sharing rows: {0,2,4,6} / {1,3,5,7}
+    const uint32_t lane_base = ((warp & 3) * 32u) << 16;
+    const uint32_t l_p_full0 = ptx::mapa(bar(bars.p_full[0]), 0);
+    const uint32_t l_p_full1 = ptx::mapa(bar(bars.p_full[1]), 0);
     const float NEG_INF = -INFINITY;
+    // softmax domain: fast mode works on raw scores (mul = scale*log2e), general on scaled+biased
+    const float mul = (MODE == kModeFast) ? p.scale_log2 : 1.0f;
     uint32_t g = 0;
     for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
       const int mt = item % p.n_mtiles;
@@ -273,28 +312,32 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t sbuf = g & 1;
         ptx::mbar_wait(bar(bars.s_full[sbuf]), (g >> 1) & 1);
         ptx::tc_fence_after();
-        uint32_t sr[64];
-        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf, sr);
-        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32, sr + 32);
+        uint32_t sr[32];
+        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32 * ch, sr);
         ptx::tmem_wait_ld();
-        float x[64];
-        const int key0 = i * 128 + 64 * (int)kh;
-        if (p.bias_kind == 0) {
+        float x[32];
+        const int key0 = i * 128 + 64 * (int)kh + 32 * (int)ch;
+        if constexpr (MODE == kModeFast) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) x[j] = __uint_as_float(sr[j]) * p.scale_log2;
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]);
         } else {
-          const int64_t boff = (int64_t)b * p.bias_stride[0] + (int64_t)h * p.bias_stride[1] +
-                               (int64_t)(gq < p.seqlen_q ? gq : 0) * p.bias_stride[2];
+          if (p.bias_kind == 0) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            const int key = key0 + j;
-            float bv = 0.f;
-            if (key < p.seqlen_kv) {
-              if (p.bias_kind == 1) bv = reinterpret_cast<const float*>(p.bias)[boff + key];
-              else if (BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[boff + key]);
-              else bv = __half2float(reinterpret_cast<const __half*>(p.bias)[boff + key]);
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]) * p.scale_log2;
+          } else {
+            const int64_t boff = (int64_t)b * p.bias_stride[0] + (int64_t)h * p.bias_stride[1] +
+                                 (int64_t)(gq < p.seqlen_q ? gq : 0) * p.bias_stride[2];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int key = key0 + j;
+              float bv = 0.f;
+              if (key < p.seqlen_kv) {
+                if (p.bias_kind == 1) bv = reinterpret_cast<const float*>(p.bias)[boff + key];
+                else if (BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[boff + key]);
+                else bv = __half2float(reinterpret_cast<const __half*>(p.bias)[boff + key]);
+              }
+              x[j] = fmaf(__uint_as_float(sr[j]), p.scale_log2, bv * 1.4426950408889634f);
             }
-            x[j] = fmaf(__uint_as_float(sr[j]), p.scale_log2, bv * 1.4426950408889634f);
           }
         }
         const bool tail = (i * 128 + 128 > p.seqlen_kv);
@@ -302,60 +345,74 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (tail || diag) {
           const int lim = p.causal ? (causal_lim < p.seqlen_kv - 1 ? causal_lim : p.seqlen_kv - 1) : p.seqlen_kv - 1;
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
+          for (int j = 0; j < 32; ++j)
             if (key0 + j > lim) x[j] = NEG_INF;
         }
-        float tmax = x[0];
-#pragma unroll
-        for (int j = 1; j < 64; ++j) tmax = fmaxf(tmax, x[j]);
-        xch[sbuf][t] = tmax;
-        ptx::named_bar_sync(1, 128);
-        tmax = fmaxf(tmax, xch[sbuf][t ^ 64]);
+        // local max: 4 independent chains of 3-input max
+        float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
+        float mx2 = fmax3(x[6], x[7], x[8]), mx3 = fmax3(x[9], x[10], x[11]);
+        mx0 = fmax3(mx0, x[12], x[13]); mx1 = fmax3(mx1, x[14], x[15]);
+        mx2 = fmax3(mx2, x[16], x[17]); mx3 = fmax3(mx3, x[18], x[19]);
+        mx0 = fmax3(mx0, x[20], x[21]); mx1 = fmax3(mx1, x[22], x[23]);
+        mx2 = fmax3(mx2, x[24], x[25]); mx3 = fmax3(mx3, x[26], x[27]);
+        mx0 = fmax3(mx0, x[28], x[29]); mx1 = fmax3(mx1, x[30], x[31]);
+        float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3);
+        xch[sbuf][slot][row] = tmax;
+        ptx::named_bar_sync(1 + rgrp, 128);
+        tmax = fmaxf(fmax3(xch[sbuf][0][row], xch[sbuf][1][row], xch[sbuf][2][row]), xch[sbuf][3][row]);
         // lazy rescale: keep the stale max while the true max is < 8 (log2 units) above it
         // (/root/reference/csrc/cuffpa/native/prefill.cuh:719-738, common.cuh:14-18)
         const float m_new = fmaxf(m, tmax);
-        const bool upd = (m_new - m) > 8.0f;  // also true for -inf -> finite; false for -inf -> -inf
+        const bool upd = (m_new - m) * mul > 8.0f;  // true for -inf -> finite; false for -inf -> -inf
         const float m_use = upd ? m_new : m;
         const bool need_rescale = upd && (m != NEG_INF);
         const float m_safe = (m_use == NEG_INF) ? 0.f : m_use;
-        float lsum = 0.f;
-        uint32_t pk[32];
-        if constexpr (DROPOUT) {
-          // dropout: keep iff u > p; row sum uses the un-dropped probabilities
+        const float neg_mc = -m_safe * mul;
+        float factor = 1.f;
+        if (need_rescale) factor = exp2f((m - m_use) * mul);
+        uint32_t pk[16];
+        float lsum;
+        if constexpr (MODE == kModeDropout) {
+          // keep iff u > p; the row sum uses the un-dropped probabilities
           // (/root/reference/csrc/cuffpa/native/prefill.cuh:506-546)
           const float inv_keep = 1.f / (1.f - p.dropout_p);
           const uint64_t ebase = p.philox_offset +
               ((uint64_t)((int64_t)b * p.heads_q + h) * (uint64_t)p.seqlen_q + (uint64_t)(gq < p.seqlen_q ? gq : 0)) * (uint64_t)p.seqlen_kv +
               (uint64_t)key0;
+          lsum = 0.f;
 #pragma unroll
-          for (int j4 = 0; j4 < 64; j4 += 4) {
-            // 4 consecutive element offsets may straddle two Philox quads when ebase % 4 != 0
-            float pv[4];
+          for (int j2 = 0; j2 < 32; j2 += 2) {
+            float pv[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float e = ptx::ex2_approx(x[j4 + u] - m_safe);
+            for (int u = 0; u < 2; ++u) {
+              const float e = exp2f(fmaf(x[j2 + u], mul, neg_mc));
               lsum += e;
-              const uint64_t eo = ebase + (uint64_t)(j4 + u);
+              const uint64_t eo = ebase + (uint64_t)(j2 + u);
               const uint4 r4 = philox4x32_10(p.philox_seed, eo >> 2);
               const uint32_t sel = (uint32_t)(eo & 3);
               const uint32_t rv = sel == 0 ? r4.x : sel == 1 ? r4.y : sel == 2 ? r4.z : r4.w;
               const float uni = ((float)rv + 1.0f) * 2.3283064365386963e-10f;
               pv[u] = (uni > p.dropout_p) ? e * inv_keep : 0.f;
             }
-            pk[(j4 >> 1)] = BF16 ? ptx::pack_bf16x2(pv[0], pv[1]) : ptx::pack_f16x2(pv[0], pv[1]);
-            pk[(j4 >> 1) + 1] = BF16 ? ptx::pack_bf16x2(pv[2], pv[3]) : ptx::pack_f16x2(pv[2], pv[3]);
+            pk[j2 >> 1] = BF16 ? ptx::pack_bf16x2(pv[0], pv[1]) : ptx::pack_f16x2(pv[0], pv[1]);
           }
         } else {
+          const float2 mul2 = make_float2(mul, mul), nm2 = make_float2(neg_mc, neg_mc);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 64; j += 2) {
-            const float e0 = ptx::ex2_approx(x[j] - m_safe);
-            const float e1 = ptx::ex2_approx(x[j + 1] - m_safe);
-            lsum += e0 + e1;
-            pk[j >> 1] = BF16 ? ptx::pack_bf16x2(e0, e1) : ptx::pack_f16x2(e0, e1);
+          for (int j = 0; j < 32; j += 4) {
+            const float2 a0 = ffma2(make_float2(x[j], x[j + 1]), mul2, nm2);
+            const float2 a1 = ffma2(make_float2(x[j + 2], x[j + 3]), mul2, nm2);
+            const float2 e0 = make_float2(exp2f(a0.x), exp2f(a0.y));
+            const float2 e1 = make_float2(exp2f(a1.x), exp2f(a1.y));
+            acc0 = fadd2(acc0, e0);
+            acc1 = fadd2(acc1, e1);
+            pk[j >> 1] = BF16 ? ptx::pack_bf16x2(e0.x, e0.y) : ptx::pack_f16x2(e0.x, e0.y);
+            pk[(j >> 1) + 1] = BF16 ? ptx::pack_bf16x2(e1.x, e1.y) : ptx::pack_f16x2(e1.x, e1.y);
           }
+          acc0 = fadd2(acc0, acc1);
+          lsum = acc0.x + acc0.y;
         }
-        float factor = 1.f;
-        if (need_rescale) factor = ptx::ex2_approx(m - m_use);
         l = l * factor + lsum;
         m = m_use;
 
@@ -364,19 +421,19 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         {
           const uint32_t prow = sP + sbuf * 16384 + kh * 8192 + row * 128;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t addr = prow + ((c ^ (row & 7)) << 4);
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = prow + (((4 * ch + c) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
                          "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
                          : "memory");
           }
         }
         if (__any_sync(0xffffffffu, need_rescale)) {
-          // O may only be touched once PV of tile g-1 has retired
+          // O may only be touched once PV of tile g-1 has retired; each warpgroup scales half the columns
           ptx::mbar_wait(bar(bars.p_empty[(g - 1) & 1]), ((g - 1) >> 1) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int c0 = 0; c0 < Cfg::O_COLS; c0 += 32) {
+          for (int c0 = (int)ch * (Cfg::O_COLS / 2); c0 < (int)(ch + 1) * (Cfg::O_COLS / 2); c0 += 32) {
             uint32_t orr[32];
             ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
             ptx::tmem_wait_ld();
@@ -389,7 +446,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
-        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(l_p_full[sbuf]);
+        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(sbuf ? l_p_full1 : l_p_full0);
       }
 
       // ---------------- epilogue: O / l -> global, LSE ----------------
@@ -397,9 +454,12 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t gl = g - 1;
         ptx::mbar_wait(bar(bars.p_empty[gl & 1]), (gl >> 1) & 1);
         ptx::tc_fence_after();
-        xl[t] = l;
-        ptx::named_bar_sync(1, 128);
-        const float l_tot = l + xl[t ^ 64];
+        // row-sum exchange reuses the max-exchange buffer of the last tile: every thread of the
+        // row group finished reading it before PV(gl) could retire (p_full precedes p_empty).
+        float (*xl)[64] = xch[gl & 1];
+        xl[slot][row] = l;
+        ptx::named_bar_sync(1 + rgrp, 128);
+        const float l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
         const bool row_ok = gq < p.seqlen_q;
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
@@ -407,8 +467,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
         for (int s = 0; s < Cfg::NSLICE; ++s) {
           const int ns = Cfg::slice_n(s);
+          const int half = ns / 4;  // columns of this slice handled by each warpgroup
 #pragma unroll 1
-          for (int c0 = 0; c0 < ns / 2; c0 += 32) {
+          for (int c0 = (int)ch * half; c0 < (int)(ch + 1) * half; c0 += 32) {
             uint32_t orr[32];
             ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
             ptx::tmem_wait_ld();
@@ -431,9 +492,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
         }
-        if (p.lse != nullptr && kh == 0 && row_ok) {
+        if (p.lse != nullptr && slot == 0 && row_ok) {
           // natural-log LSE; rows without any visible key: O = 0, LSE = -inf
-          const float lse = (l_tot > 0.f) ? (m + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
+          const float lse = (l_tot > 0.f) ? (m * mul + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
           p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
         }
         ptx::tc_fence_before();
@@ -443,17 +504,17 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   ptx::tc_fence_before();
   ptx::cluster_sync();
-  if (warp == 4) ptx::tmem_dealloc<CG>(tmem, 512);
+  if (warp == kMmaWarp) ptx::tmem_dealloc<CG>(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
-// host launcher
+// host launcher pieces (instantiated per dtype in ffpa_fwd_bf16.cu / ffpa_fwd_f16.cu)
 // ------------------------------------------------------------------------------------------------
-template <int NQK, bool BF16, bool DROPOUT>
+template <int NQK, bool BF16, int MODE>
 static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                           const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
   using Cfg = FwdCfg<NQK>;
-  auto kern = ffpa_fwd_kernel<NQK, BF16, DROPOUT>;
+  auto kern = ffpa_fwd_kernel<NQK, BF16, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN);
@@ -467,66 +528,28 @@ static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CU
   return FFPA_OK;
 }
 
-template <bool BF16, bool DROPOUT>
+template <bool BF16, int MODE>
 static int dispatch_nqk(int nqk, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                         const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
   switch (nqk) {
-    case 1: return launch_variant<1, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
-    case 2: return launch_variant<2, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
-    case 3: return launch_variant<3, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
-    case 4: return launch_variant<4, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
-    case 5: return launch_variant<5, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
-    case 6: return launch_variant<6, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
-    case 7: return launch_variant<7, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
-    case 8: return launch_variant<8, BF16, DROPOUT>(mq, mk, mv, kp, nclusters, stream);
+    case 1: return launch_variant<1, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 2: return launch_variant<2, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 3: return launch_variant<3, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 4: return launch_variant<4, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 5: return launch_variant<5, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 6: return launch_variant<6, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 7: return launch_variant<7, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 8: return launch_variant<8, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
     default: return set_error(FFPA_ERR_UNSUPPORTED, "head_dim > 512 not supported by this kernel");
   }
 }
 
-static bool make_map(CUtensorMap* m, const void* base, const int64_t* stride, int B, int H, int N,
-                     int D, uint32_t box_d, uint32_t box_n) {
-  uint64_t dims[4] = {(uint64_t)D, (uint64_t)N, (uint64_t)H, (uint64_t)B};
-  uint64_t str[3] = {(uint64_t)stride[2] * 2, (uint64_t)stride[1] * 2, (uint64_t)stride[0] * 2};
-  // size-1 dims may carry arbitrary (even 0) strides; TMA wants multiples of 16 and > 0
-  for (int i = 0; i < 3; ++i)
-    if (dims[i + 1] == 1) str[i] = (uint64_t)D * 2 * (i >= 1 ? (uint64_t)N : 1) * (i >= 2 ? (uint64_t)H : 1);
-  uint32_t box[4] = {box_d, box_n, 1, 1};
-  return tmap::encode_sw128(m, const_cast<void*>(base), 2, 4, dims, str, box);
-}
-
-int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
-  const int D = a.head_dim;
-  const int nqk = (D + 63) / 64;
-  CUtensorMap mq, mk, mv;
-  if (!make_map(&mq, a.q, a.q_stride, a.batch, a.heads_q, a.seqlen_q, D, 64, 64) ||
-      !make_map(&mk, a.k, a.k_stride, a.batch, a.heads_kv, a.seqlen_kv, D, 64, 64) ||
-      !make_map(&mv, a.v, a.v_stride, a.batch, a.heads_kv, a.seqlen_kv, D, 64, 128))
-    return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed (strides must be multiples of 8 elements, base 16-byte aligned)");
-
-  FwdKernelParams kp{};
-  kp.o = a.o;
-  kp.lse = a.lse;
-  kp.bias = a.bias;
-  for (int i = 0; i < 3; ++i) kp.o_stride[i] = a.o_stride[i];
-  for (int i = 0; i < 4; ++i) kp.bias_stride[i] = a.bias_stride[i];
-  kp.batch = a.batch; kp.heads_q = a.heads_q; kp.heads_kv = a.heads_kv;
-  kp.seqlen_q = a.seqlen_q; kp.seqlen_kv = a.seqlen_kv; kp.head_dim = D;
-  kp.causal = a.causal; kp.bias_kind = a.bias_kind;
-  kp.scale_log2 = a.softmax_scale * 1.4426950408889634f;
-  kp.dropout_p = a.dropout_p;
-  kp.philox_seed = a.philox_seed; kp.philox_offset = a.philox_offset;
-  kp.n_mtiles = (a.seqlen_q + 127) / 128;
-  kp.n_items = kp.n_mtiles * a.batch * a.heads_q;
-
-  int nsm = sm_count();
-  int nclusters = nsm / 2;
-  if (nclusters > kp.n_items) nclusters = kp.n_items;
-  const bool drop = a.dropout_p > 0.f;
-  if (a.dtype == FFPA_DTYPE_BF16)
-    return drop ? dispatch_nqk<true, true>(nqk, mq, mk, mv, kp, nclusters, stream)
-                : dispatch_nqk<true, false>(nqk, mq, mk, mv, kp, nclusters, stream);
-  return drop ? dispatch_nqk<false, true>(nqk, mq, mk, mv, kp, nclusters, stream)
-              : dispatch_nqk<false, false>(nqk, mq, mk, mv, kp, nclusters, stream);
+template <bool BF16>
+int dispatch_fwd_dtype(int nqk, int mode, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                       const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
+  if (mode == kModeFast) return dispatch_nqk<BF16, kModeFast>(nqk, mq, mk, mv, kp, nclusters, stream);
+  if (mode == kModeGeneral) return dispatch_nqk<BF16, kModeGeneral>(nqk, mq, mk, mv, kp, nclusters, stream);
+  return dispatch_nqk<BF16, kModeDropout>(nqk, mq, mk, mv, kp, nclusters, stream);
 }
 
 }  // namespace ffpa
