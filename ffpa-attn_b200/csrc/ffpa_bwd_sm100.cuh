@@ -1,0 +1,538 @@
+// B200 (sm_100a) attention backward: three tcgen05 kernels built from one skeleton.
+//
+// Math (reference: /root/reference/src/ffpa_attn/triton/_ffpa_bwd.py:236-306, 692-855; the split
+// into dQ / dK / dV launches follows what the reference's SM100 backend does,
+// /root/reference/src/ffpa_attn/cute/_ffpa_bwd_sm100.py:301-484):
+//   delta = rowsum(dO * O);  P = exp(scale*S - LSE);  dP = dO V^T;  dS = P * (dP - delta)
+//   dQ = scale * dS K;  dK = scale * dS^T Q;  dV = P^T dO;  GQA: dK/dV sum over the head group.
+//
+// Skeleton ("stationary rows x streamed column tiles", 2-CTA cluster owns 128 stationary rows):
+//   GEMM1  S  = A1 * B1^T          A1 resident (K-major), B1 streamed (K-major)      -> TMEM
+//   GEMM2  dP = A2 * B2^T          (dQ / dK kinds only)                              -> TMEM
+//   elementwise warps:  T = f(S, dP, stats)  -> bf16/fp16 -> SMEM (K-major A operand)
+//   GEMM3  ACC += T * B3           B3 streamed as an MN-major operand (row-major [cols x d])
+//   kind dQ: rows = queries, cols = keys   A1=Q  B1=K  A2=dO B2=V  T=dS    B3=K
+//   kind dK: rows = keys,    cols = queries A1=K  B1=Q  A2=V  B2=dO T=dS^T  B3=Q
+//   kind dV: rows = keys,    cols = queries A1=K  B1=Q              T=P^T   B3=dO
+// TMEM (D=512): ACC 256 columns (lane folded, 4 N=128 slices), S 2x64, dP 2x64 = 512.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cmath>
+#include "ffpa_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace ffpa {
+namespace bwd {
+
+constexpr int kSoftmaxWarps = 8;
+constexpr int kMmaWarp = 8;
+constexpr int kTmaWarp = 9;
+constexpr int kThreads = 320;
+constexpr int kSmemLimit = 232448;
+
+constexpr int kKindDQ = 0;
+constexpr int kKindDK = 1;
+constexpr int kKindDV = 2;
+
+
+template <int NQK, int KIND>
+struct BwdCfg {
+  static constexpr bool HAS_DP = (KIND != kKindDV);
+  static constexpr int HD = NQK * 64;
+  static constexpr int DVP = ((HD + 127) / 128) * 128;
+  static constexpr int NSL = DVP / 128;                    // N=128 slices of the accumulator
+  static constexpr int ACC_COLS = DVP / 2;
+  static constexpr int KST = (NQK + 1) / 2;                // 16 KB K-major stages per streamed tile and operand
+  static constexpr int S_BASE = 256, DP_BASE = 384;
+  static constexpr int A_BYTES = NQK * 8192;
+  static constexpr int NA = HAS_DP ? 2 : 1;
+  static constexpr int T_BYTES = 2 * 16384;
+  static constexpr int kBudget = kSmemLimit - 3072;
+  static constexpr int kRaw = (kBudget - NA * A_BYTES - T_BYTES) / 16384;
+  static constexpr int NST = kRaw > 12 ? 12 : kRaw;        // unified ring of 16 KB stages
+  static constexpr int SMEM_DYN = NA * A_BYTES + T_BYTES + NST * 16384;
+  static_assert(NST >= 3, "not enough shared memory for the streaming ring");
+  static_assert(ACC_COLS <= 256, "backward kernels support head_dim <= 512");
+};
+
+struct Barriers {
+  uint64_t a_full, a_empty;
+  uint64_t r_full[12], r_empty[12];
+  uint64_t s_full[2];
+  uint64_t t_full[2], t_empty[2];
+};
+
+// streamed-tile range of an item
+struct TileRange { int first, count; };
+
+template <int KIND>
+__device__ __forceinline__ TileRange col_tiles(const BwdKernelParams& p, int r0) {
+  if (KIND == kKindDQ) {  // rows = queries starting at r0; columns = KV tiles
+    int tc = (p.seqlen_kv + 127) >> 7;
+    if (p.causal) {
+      int lim = ((r0 + 127 + (p.seqlen_kv - p.seqlen_q)) >> 7) + 1;
+      tc = lim < tc ? lim : tc;
+    }
+    return {0, tc < 1 ? 1 : tc};
+  } else {  // rows = keys starting at r0; columns = query tiles (per head of the group)
+    const int tq = (p.seqlen_q + 127) >> 7;
+    int first = 0;
+    if (p.causal) {
+      const int qmin = r0 - (p.seqlen_kv - p.seqlen_q);  // first query row that sees key r0
+      first = qmin > 0 ? (qmin >> 7) : 0;
+      if (first > tq) first = tq;
+    }
+    return {first, tq - first};
+  }
+}
+
+template <int NQK, bool BF16, int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+                const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
+                const __grid_constant__ CUtensorMap map_b3, const BwdKernelParams p) {
+  using Cfg = BwdCfg<NQK, KIND>;
+  constexpr int CG = 2;
+  constexpr bool HAS_DP = Cfg::HAS_DP;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ Barriers bars;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  const uint32_t sA1 = smem_base;
+  const uint32_t sA2 = sA1 + Cfg::A_BYTES;                  // only when HAS_DP
+  const uint32_t sT = sA1 + Cfg::NA * Cfg::A_BYTES;
+  const uint32_t sR = sT + Cfg::T_BYTES;
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t cluster = blockIdx.x >> 1;
+  const uint32_t nclusters = gridDim.x >> 1;
+  auto bar = [](uint64_t& b) { return ptx::smem_u32(&b); };
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar(bars.a_full), 1);
+    ptx::mbar_init(bar(bars.a_empty), 1);
+    for (int i = 0; i < 12; ++i) { ptx::mbar_init(bar(bars.r_full[i]), 1); ptx::mbar_init(bar(bars.r_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar(bars.s_full[i]), 1);
+      ptx::mbar_init(bar(bars.t_full[i]), 2 * kSoftmaxWarps);
+      ptx::mbar_init(bar(bars.t_empty[i]), 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == kTmaWarp && ptx::elect_one()) {
+    ptx::prefetch_tmap(&map_a1); ptx::prefetch_tmap(&map_b1); ptx::prefetch_tmap(&map_b3);
+    if (HAS_DP) { ptx::prefetch_tmap(&map_a2); ptx::prefetch_tmap(&map_b2); }
+  }
+  if (warp == kMmaWarp) {
+    ptx::tmem_alloc<CG>(ptx::smem_u32(&tmem_slot), 512);
+    ptx::tmem_relinquish<CG>();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const int group = p.heads_q / p.heads_kv;
+  // heads: dQ kind iterates query heads; dK/dV kinds iterate KV heads and loop the group inside
+  const int heads_it = (KIND == kKindDQ) ? p.heads_q : p.heads_kv;
+  const int n_inner = (KIND == kKindDQ) ? 1 : group;
+
+  if (warp == kTmaWarp) {
+    // =========================================== TMA producer ===================================
+    if (ptx::elect_one()) {
+      uint32_t rc = 0, it = 0;
+      const uint32_t l_a_full = ptx::mapa(bar(bars.a_full), 0);
+      auto load_kmajor = [&](const CUtensorMap* m, int c_row0, int hh, int bb) {
+        // KST stages of [64 rows(this CTA) x 128 d]
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KST; ++ks) {
+          const uint32_t stage = rc % Cfg::NST, n = rc / Cfg::NST;
+          ptx::mbar_wait(bar(bars.r_empty[stage]), (n & 1) ^ 1);
+          const int nb = (NQK - 2 * ks) >= 2 ? 2 : 1;
+          if (rank == 0) ptx::mbar_expect_tx(bar(bars.r_full[stage]), 2 * nb * 8192);
+          const uint32_t l_full = ptx::mapa(bar(bars.r_full[stage]), 0);
+          for (int bx = 0; bx < nb; ++bx)
+            ptx::tma_load_4d_2sm(sR + stage * 16384 + bx * 8192, m, l_full, (2 * ks + bx) * 64, c_row0 + 64 * (int)rank, hh, bb);
+          ++rc;
+        }
+      };
+      auto load_mnmajor = [&](const CUtensorMap* m, int c_row0, int hh, int bb) {
+        // NSL stages of [128 rows x 64 d(this CTA's half of the 128-wide slice)]
+#pragma unroll
+        for (int s = 0; s < Cfg::NSL; ++s) {
+          const uint32_t stage = rc % Cfg::NST, n = rc / Cfg::NST;
+          ptx::mbar_wait(bar(bars.r_empty[stage]), (n & 1) ^ 1);
+          if (rank == 0) ptx::mbar_expect_tx(bar(bars.r_full[stage]), 2 * 16384);
+          const uint32_t l_full = ptx::mapa(bar(bars.r_full[stage]), 0);
+          ptx::tma_load_4d_2sm(sR + stage * 16384, m, l_full, 128 * s + 64 * (int)rank, c_row0, hh, bb);
+          ++rc;
+        }
+      };
+      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
+        const int rt = item % p.n_rtiles;
+        const int bh = item / p.n_rtiles;
+        const int hs = bh % heads_it, b = bh / heads_it;  // head of the stationary operand
+        const int r0 = rt * 128;
+        const TileRange tr = col_tiles<KIND>(p, r0);
+        const int T = tr.count * n_inner;
+        if (T <= 0) continue;
+        // stationary operands
+        ptx::mbar_wait(bar(bars.a_empty), (it & 1) ^ 1);
+        if (rank == 0) ptx::mbar_expect_tx(bar(bars.a_full), 2 * Cfg::NA * Cfg::A_BYTES);
+        const int ha = hs;  // A tensors are indexed by their own head (q head for dQ, kv head for dK/dV)
+#pragma unroll
+        for (int jb = 0; jb < NQK; ++jb) {
+          ptx::tma_load_4d_2sm(sA1 + jb * 8192, &map_a1, l_a_full, jb * 64, r0 + 64 * (int)rank, ha, b);
+          if (HAS_DP) ptx::tma_load_4d_2sm(sA2 + jb * 8192, &map_a2, l_a_full, jb * 64, r0 + 64 * (int)rank, ha, b);
+        }
+        for (int step = 0; step <= T; ++step) {
+          if (step < T) {
+            const int gi = step / tr.count, ci = tr.first + step % tr.count;
+            const int hb = (KIND == kKindDQ) ? hs / group : hs * group + gi;  // head of the streamed operands
+            load_kmajor(&map_b1, ci * 128, hb, b);
+            if (HAS_DP) load_kmajor(&map_b2, ci * 128, hb, b);
+          }
+          if (step >= 1) {
+            const int st = step - 1;
+            const int gi = st / tr.count, ci = tr.first + st % tr.count;
+            const int hb = (KIND == kKindDQ) ? hs / group : hs * group + gi;
+            load_mnmajor(&map_b3, ci * 128, hb, b);
+          }
+        }
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // =========================================== MMA issuer (leader CTA) ========================
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t fmt = BF16 ? 1u : 0u;
+      constexpr uint32_t idesc_s = ptx::make_idesc(fmt, fmt, 0, 0, 128, 128);
+      constexpr uint32_t idesc_acc = ptx::make_idesc(fmt, fmt, 0, 1, 128, 128);
+      uint32_t rc = 0, it = 0, g = 0, gp = 0;
+      auto gemm_kmajor = [&](uint32_t sA, uint32_t d_tmem) {
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KST; ++ks) {
+          const uint32_t stage = rc % Cfg::NST, n = rc / Cfg::NST;
+          ptx::mbar_wait(bar(bars.r_full[stage]), n & 1);
+          ptx::tc_fence_after();
+          const int nb = (NQK - 2 * ks) >= 2 ? 2 : 1;
+          for (int bx = 0; bx < nb; ++bx) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t ad = ptx::make_smem_desc_sw128(sA + (2 * ks + bx) * 8192 + k4 * 32, 16, 1024);
+              const uint64_t bd = ptx::make_smem_desc_sw128(sR + stage * 16384 + bx * 8192 + k4 * 32, 16, 1024);
+              ptx::umma_f16_ss<CG>(d_tmem, ad, bd, idesc_s, (ks | bx | k4) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit_mc<CG>(bar(bars.r_empty[stage]), 0x3);
+          ++rc;
+        }
+      };
+      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
+        const int rt = item % p.n_rtiles;
+        const TileRange tr = col_tiles<KIND>(p, rt * 128);
+        const int T = tr.count * n_inner;
+        if (T <= 0) continue;
+        ptx::mbar_wait(bar(bars.a_full), it & 1);
+        ptx::tc_fence_after();
+        for (int step = 0; step <= T; ++step) {
+          if (step < T) {
+            const uint32_t sbuf = g & 1;
+            gemm_kmajor(sA1, tmem + Cfg::S_BASE + 64 * sbuf);
+            if (HAS_DP) gemm_kmajor(sA2, tmem + Cfg::DP_BASE + 64 * sbuf);
+            ptx::umma_commit_mc<CG>(bar(bars.s_full[sbuf]), 0x3);
+            if (step == T - 1) ptx::umma_commit_mc<CG>(bar(bars.a_empty), 0x3);
+            ++g;
+          }
+          if (step >= 1) {
+            const uint32_t tbuf = gp & 1;
+            ptx::mbar_wait_cluster(bar(bars.t_full[tbuf]), (gp >> 1) & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < Cfg::NSL; ++s) {
+              const uint32_t stage = rc % Cfg::NST, n = rc / Cfg::NST;
+              ptx::mbar_wait(bar(bars.r_full[stage]), n & 1);
+              ptx::tc_fence_after();
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t ad = ptx::make_smem_desc_sw128(sT + tbuf * 16384 + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
+                const uint64_t bd = ptx::make_smem_desc_sw128(sR + stage * 16384 + kk * 2048, 16384, 1024);
+                ptx::umma_f16_ss<CG>(tmem + 64 * s, ad, bd, idesc_acc, (step > 1 || kk > 0) ? 1u : 0u);
+              }
+              ptx::umma_commit_mc<CG>(bar(bars.r_empty[stage]), 0x3);
+              ++rc;
+            }
+            ptx::umma_commit_mc<CG>(bar(bars.t_empty[tbuf]), 0x3);
+            ++gp;
+          }
+        }
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================== elementwise warps + epilogue ===================
+    const uint32_t t = threadIdx.x;
+    const uint32_t lane128 = t & 127;
+    const uint32_t row = lane128 & 63;
+    const uint32_t kh = lane128 >> 6;   // 64-column half of the streamed tile / column half of ACC
+    const uint32_t ch = t >> 7;         // 32-column half inside the S stage
+    const uint32_t lane_base = ((warp & 3) * 32u) << 16;
+    const uint32_t l_t_full0 = ptx::mapa(bar(bars.t_full[0]), 0);
+    const uint32_t l_t_full1 = ptx::mapa(bar(bars.t_full[1]), 0);
+    const int off = p.seqlen_kv - p.seqlen_q;
+    uint32_t g = 0;
+    for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
+      const int rt = item % p.n_rtiles;
+      const int bh = item / p.n_rtiles;
+      const int hs = bh % heads_it, b = bh / heads_it;
+      const int r0 = rt * 128;
+      const TileRange tr = col_tiles<KIND>(p, r0);
+      const int T = tr.count * n_inner;
+      const int grow = r0 + 64 * (int)rank + (int)row;  // global stationary row (query or key)
+      const bool row_ok = grow < ((KIND == kKindDQ) ? p.seqlen_q : p.seqlen_kv);
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
+                      2 * ((int64_t)b * p.out_stride[0] + (int64_t)hs * p.out_stride[1] + (int64_t)grow * p.out_stride[2]);
+      if (T <= 0) {
+        // nothing contributes (causal, keys beyond every query's window): gradient is zero
+        if (row_ok) {
+          for (int d = (int)(kh * 2 + ch) * 8; d < p.head_dim; d += 32)
+            *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(0, 0, 0, 0);
+        }
+        continue;
+      }
+      float row_lse2 = 0.f, row_delta = 0.f;
+      if (KIND == kKindDQ) {
+        const int64_t so = ((int64_t)b * p.heads_q + hs) * p.nq_pad + grow;  // grow < nq_pad always
+        row_lse2 = p.lse2[so];
+        row_delta = p.delta[so];
+      }
+      for (int i = 0; i < T; ++i, ++g) {
+        const uint32_t sbuf = g & 1;
+        const int gi = i / tr.count, ci = tr.first + i % tr.count;
+        const int col0 = ci * 128 + 64 * (int)kh + 32 * (int)ch;  // first global column of this thread
+        // column statistics (dK / dV kinds): issue the loads before waiting for the MMA
+        float4 c_lse[8], c_dl[8];
+        if (KIND != kKindDQ) {
+          const int hq = hs * group + gi;
+          const int64_t so = ((int64_t)b * p.heads_q + hq) * p.nq_pad + col0;
+          const float4* pl = reinterpret_cast<const float4*>(p.lse2 + so);
+          const float4* pd = reinterpret_cast<const float4*>(p.delta + so);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            c_lse[j] = __ldg(pl + j);
+            if (HAS_DP) c_dl[j] = __ldg(pd + j);
+          }
+        }
+        ptx::mbar_wait(bar(bars.s_full[sbuf]), (g >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t sr[32], dr[32];
+        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32 * ch, sr);
+        if (HAS_DP) ptx::tmem_ld_x32(tmem + lane_base + Cfg::DP_BASE + 64 * sbuf + 32 * ch, dr);
+        ptx::tmem_wait_ld();
+        // visibility: key <= query + off (causal), key < Nkv; padded / empty query rows carry lse2=+inf
+        int lim_lo = 0, lim_hi = 0x7fffffff;  // visible columns: lim_lo <= col <= lim_hi
+        if (KIND == kKindDQ) {
+          lim_hi = p.seqlen_kv - 1;
+          if (p.causal) { const int cl = grow + off; lim_hi = cl < lim_hi ? cl : lim_hi; }
+        } else {
+          if (p.causal) lim_lo = grow - off;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float e[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int jj = j + u;
+            float l2, dl;
+            if (KIND == kKindDQ) { l2 = row_lse2; dl = row_delta; }
+            else {
+              const float4 a = c_lse[jj >> 2];
+              l2 = (jj & 3) == 0 ? a.x : (jj & 3) == 1 ? a.y : (jj & 3) == 2 ? a.z : a.w;
+              if (HAS_DP) { const float4 d4 = c_dl[jj >> 2]; dl = (jj & 3) == 0 ? d4.x : (jj & 3) == 1 ? d4.y : (jj & 3) == 2 ? d4.z : d4.w; }
+              else dl = 0.f;
+            }
+            float pe = exp2f(fmaf(__uint_as_float(sr[jj]), p.scale_log2, -l2));
+            const int col = col0 + jj;
+            if (col < lim_lo || col > lim_hi) pe = 0.f;
+            e[u] = HAS_DP ? pe * (__uint_as_float(dr[jj]) - dl) : pe;
+          }
+          pk[j >> 1] = BF16 ? ptx::pack_bf16x2(e[0], e[1]) : ptx::pack_f16x2(e[0], e[1]);
+        }
+        ptx::mbar_wait(bar(bars.t_empty[sbuf]), ((g >> 1) & 1) ^ 1);
+        {
+          const uint32_t prow = sT + sbuf * 16384 + kh * 8192 + row * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = prow + (((4 * ch + c) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
+                         "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                         : "memory");
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(sbuf ? l_t_full1 : l_t_full0);
+      }
+      // ---------------- epilogue: ACC (x scale) -> global ----------------
+      {
+        const uint32_t gl = g - 1;
+        ptx::mbar_wait(bar(bars.t_empty[gl & 1]), (gl >> 1) & 1);
+        ptx::tc_fence_after();
+        const float mulo = (KIND == kKindDV) ? 1.f : p.scale;
+#pragma unroll
+        for (int s = 0; s < Cfg::NSL; ++s) {
+          uint32_t orr[32];
+          ptx::tmem_ld_x32(tmem + lane_base + 64 * s + 32 * ch, orr);
+          ptx::tmem_wait_ld();
+          const int d0 = 128 * s + 64 * (int)kh + 32 * (int)ch;
+          if (row_ok) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const int d = d0 + 8 * v;
+              if (d < p.head_dim) {
+                uint32_t w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float a = __uint_as_float(orr[8 * v + 2 * u]) * mulo;
+                  const float c = __uint_as_float(orr[8 * v + 2 * u + 1]) * mulo;
+                  w[u] = BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
+                }
+                *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == kMmaWarp) ptx::tmem_dealloc<CG>(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// preprocess: delta = rowsum(dO * O), lse2 = LSE * log2(e) (+inf when the row saw no key), padded
+// to a multiple of 128 rows per (b, h).  One warp per row.  (reference: _ffpa_bwd.py:236-306)
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void bwd_preprocess_kernel(const void* __restrict__ o, const void* __restrict__ d_o,
+                                      const float* __restrict__ lse, float* __restrict__ lse2,
+                                      float* __restrict__ delta, int64_t os0, int64_t os1, int64_t os2,
+                                      int64_t ds0, int64_t ds1, int64_t ds2, int B, int H, int Nq,
+                                      int nq_pad, int D) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t rowid = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int64_t total = (int64_t)B * H * nq_pad;
+  if (rowid >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int q = (int)(rowid % nq_pad);
+  const int64_t bh = rowid / nq_pad;
+  const int h = (int)(bh % H), b = (int)(bh / H);
+  if (q >= Nq) {
+    if (lane == 0) { lse2[rowid] = INFINITY; delta[rowid] = 0.f; }
+    return;
+  }
+  const uint8_t* po = reinterpret_cast<const uint8_t*>(o) + 2 * (b * os0 + h * os1 + q * os2);
+  const uint8_t* pd = reinterpret_cast<const uint8_t*>(d_o) + 2 * (b * ds0 + h * ds1 + q * ds2);
+  float acc = 0.f;
+  for (int d = lane * 8; d < D; d += 256) {
+    const uint4 a = *reinterpret_cast<const uint4*>(po + 2 * d);
+    const uint4 c = *reinterpret_cast<const uint4*>(pd + 2 * d);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float a0, a1, c0, c1;
+      if (BF16) {
+        a0 = __uint_as_float(aw[u] << 16); a1 = __uint_as_float(aw[u] & 0xffff0000u);
+        c0 = __uint_as_float(cw[u] << 16); c1 = __uint_as_float(cw[u] & 0xffff0000u);
+      } else {
+        const __half2 ha = *reinterpret_cast<const __half2*>(&aw[u]);
+        const __half2 hc = *reinterpret_cast<const __half2*>(&cw[u]);
+        a0 = __low2float(ha); a1 = __high2float(ha); c0 = __low2float(hc); c1 = __high2float(hc);
+      }
+      acc = fmaf(a0, c0, acc);
+      acc = fmaf(a1, c1, acc);
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    const float l = lse[bh * Nq + q];
+    lse2[rowid] = (l == -INFINITY) ? INFINITY : l * 1.4426950408889634f;
+    delta[rowid] = acc;
+  }
+}
+
+
+template <int NQK, bool BF16, int KIND>
+static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
+                              const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp,
+                              int nclusters, cudaStream_t stream) {
+  using Cfg = BwdCfg<NQK, KIND>;
+  auto kern = ffpa_bwd_kernel<NQK, BF16, KIND>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN);
+    if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(bwd smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(a1, a2, b1, b2, b3, kp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "backward launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return FFPA_OK;
+}
+
+template <bool BF16, int KIND>
+static int dispatch_bwd_nqk(int nqk, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
+                            const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp,
+                            int nclusters, cudaStream_t stream) {
+  switch (nqk) {
+    case 1: return launch_bwd_variant<1, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 2: return launch_bwd_variant<2, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 3: return launch_bwd_variant<3, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 4: return launch_bwd_variant<4, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 5: return launch_bwd_variant<5, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 6: return launch_bwd_variant<6, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 7: return launch_bwd_variant<7, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 8: return launch_bwd_variant<8, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    default: return set_error(FFPA_ERR_UNSUPPORTED, "backward supports head_dim <= 512");
+  }
+}
+
+// kind: 0 dQ, 1 dK, 2 dV
+template <bool BF16>
+int dispatch_bwd_dtype(int nqk, int kind, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
+                       const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp, int nclusters,
+                       cudaStream_t stream) {
+  if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+  if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+  return dispatch_bwd_nqk<BF16, kKindDV>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+}
+
+template <bool BF16>
+int launch_preprocess(const ffpa_bwd_params& a, float* lse2, float* delta, int nq_pad, cudaStream_t stream) {
+  const int64_t rows = (int64_t)a.batch * a.heads_q * nq_pad;
+  const int wpb = 8;
+  const int64_t blocks = (rows + wpb - 1) / wpb;
+  bwd_preprocess_kernel<BF16><<<dim3((unsigned)blocks), dim3(wpb * 32), 0, stream>>>(
+      a.o, a.d_o, a.lse, lse2, delta, a.o_stride[0], a.o_stride[1], a.o_stride[2], a.do_stride[0],
+      a.do_stride[1], a.do_stride[2], a.batch, a.heads_q, a.seqlen_q, nq_pad, a.head_dim);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "backward preprocess launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return FFPA_OK;
+}
+
+}  // namespace bwd
+}  // namespace ffpa

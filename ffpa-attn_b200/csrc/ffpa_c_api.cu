@@ -102,21 +102,44 @@ int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream) {
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "q/k/v/o base pointers must be 16-byte aligned");
   if (p->fp8 || g_impl_hint.load() == FFPA_IMPL_CUTE_TMA_FP4)
     return set_error(FFPA_ERR_UNSUPPORTED, p->fp8 ? "FP8 forward is not built into this library yet" : "FP4 path is not implemented on sm_100a");
-  if (p->head_dim > 512)
-    return set_error(FFPA_ERR_UNSUPPORTED, "head_dim %d > 512 is not built into this library yet", p->head_dim);
   return launch_fwd_sm100(*p, static_cast<cudaStream_t>(stream));
 }
 
 int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream) {
-  (void)stream;
   if (!p) return set_error(FFPA_ERR_INVALID_ARGUMENT, "params is NULL");
-  return set_error(FFPA_ERR_UNSUPPORTED, "backward is not built into this library yet");
+  if (int e = check_device()) return e;
+  if (!p->q || !p->k || !p->v || !p->o || !p->lse || !p->d_o || !p->dq || !p->dk || !p->dv)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "q/k/v/o/lse/dO/dQ/dK/dV must be non-NULL device pointers");
+  if (p->dtype != FFPA_DTYPE_F16 && p->dtype != FFPA_DTYPE_BF16)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "dtype must be fp16 or bf16");
+  if (p->batch <= 0 || p->heads_q <= 0 || p->heads_kv <= 0 || p->seqlen_q <= 0 || p->seqlen_kv <= 0 || p->head_dim <= 0)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "all sizes must be positive");
+  if (p->heads_q % p->heads_kv != 0)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "Q heads (%d) must be an integer multiple of KV heads (%d)", p->heads_q, p->heads_kv);
+  if (p->head_dim % 8 != 0) return set_error(FFPA_ERR_INVALID_ARGUMENT, "head_dim must be a multiple of 8, got %d", p->head_dim);
+  if (p->causal && p->seqlen_kv < p->seqlen_q)
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "causal attention requires Nkv >= Nq");
+  if (p->head_dim > 512)
+    return set_error(FFPA_ERR_UNSUPPORTED, "backward kernels support head_dim <= 512 (got %d)", p->head_dim);
+  const int32_t qd[3] = {p->batch, p->heads_q, p->seqlen_q};
+  const int32_t kd[3] = {p->batch, p->heads_kv, p->seqlen_kv};
+  if (int e = check_strides("Q", p->q_stride, qd)) return e;
+  if (int e = check_strides("K", p->k_stride, kd)) return e;
+  if (int e = check_strides("V", p->v_stride, kd)) return e;
+  if (int e = check_strides("O", p->o_stride, qd)) return e;
+  if (int e = check_strides("dO", p->do_stride, qd)) return e;
+  if (int e = check_strides("dQ", p->dq_stride, qd)) return e;
+  if (int e = check_strides("dK", p->dk_stride, kd)) return e;
+  if (int e = check_strides("dV", p->dv_stride, kd)) return e;
+  if (!aligned16(p->q) || !aligned16(p->k) || !aligned16(p->v) || !aligned16(p->o) || !aligned16(p->d_o) ||
+      !aligned16(p->dq) || !aligned16(p->dk) || !aligned16(p->dv) || !aligned16(p->workspace))
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "all tensor base pointers must be 16-byte aligned");
+  return launch_bwd_sm100(*p, static_cast<cudaStream_t>(stream));
 }
 
 uint64_t ffpa_b200_bwd_workspace_bytes(int32_t batch, int32_t heads_q, int32_t heads_kv, int32_t seqlen_q,
                                        int32_t seqlen_kv, int32_t head_dim) {
-  (void)batch; (void)heads_q; (void)heads_kv; (void)seqlen_q; (void)seqlen_kv; (void)head_dim;
-  return 0;
+  return bwd_workspace_bytes(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
 }
 
 int ffpa_b200_set_backend_impl(int32_t impl) {
@@ -127,7 +150,7 @@ int ffpa_b200_set_backend_impl(int32_t impl) {
 }
 int32_t ffpa_b200_get_backend_impl(void) { return g_impl_hint.load(); }
 int32_t ffpa_b200_fwd_available(void) { return 1; }
-int32_t ffpa_b200_bwd_available(void) { return 0; }
+int32_t ffpa_b200_bwd_available(void) { return 1; }
 int32_t ffpa_b200_abi_version(void) { return FFPA_B200_ABI_VERSION; }
 uint64_t ffpa_b200_launch_count(void) { return g_launches.load(); }
 const char* ffpa_b200_last_error(void) { return g_err; }

@@ -48,7 +48,9 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   kp.dropout_p = a.dropout_p;
   kp.philox_seed = a.philox_seed; kp.philox_offset = a.philox_offset;
   kp.n_mtiles = (a.seqlen_q + 127) / 128;
-  kp.n_items = kp.n_mtiles * a.batch * a.heads_q;
+  const int dvp = ((nqk * 64 + 127) / 128) * 128;
+  const int npass = dvp > 768 ? 2 : 1;  // must match FwdCfg<NQK>::NPASS
+  kp.n_items = kp.n_mtiles * npass * a.batch * a.heads_q;
 
   int nclusters = sm_count() / 2;
   if (nclusters > kp.n_items) nclusters = kp.n_items;

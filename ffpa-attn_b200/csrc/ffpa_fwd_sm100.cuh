@@ -40,20 +40,26 @@ template <int NQK>
 struct FwdCfg {
   static constexpr int HD = NQK * 64;                     // padded head dim for QK^T
   static constexpr int DVP = ((HD + 127) / 128) * 128;    // padded head dim for PV / O
-  static constexpr int O_COLS = DVP / 2;                  // TMEM columns of O per CTA (lane folded)
-  static constexpr int NSLICE = (DVP + 255) / 256;        // PV N-slices (256 wide, last may be 128)
+  // O must stay TMEM-resident next to the two S stages (128 columns): at most 384 columns = 768
+  // head dims per pass. Wider heads run two passes over 512-wide O slabs, recomputing S.
+  static constexpr int NPASS = DVP > 768 ? 2 : 1;
+  static constexpr int DSLAB = NPASS == 1 ? DVP : 512;    // head dims of O per pass (last pass may be narrower)
+  static constexpr int O_COLS = DSLAB / 2;                // TMEM columns of O per CTA (lane folded)
+  static constexpr int NSLICE = (DSLAB + 255) / 256;      // max PV N-slices per pass (256 wide, last may be 128)
   static constexpr int KST = (NQK + 1) / 2;               // 16 KB K stages per KV tile
-  static constexpr int S_BASE = 256;                      // TMEM column of S[0]; S[1] = +64
+  static constexpr int S_BASE = O_COLS > 256 ? 384 : 256; // TMEM column of S[0]; S[1] = +64
   static constexpr int Q_BYTES = NQK * 8192;
   static constexpr int P_BYTES = 2 * 16384;
-  static constexpr int NVS = (HD > 256) ? 2 : 3;          // 32 KB V stages
+  static constexpr int NVS = HD > 768 ? 1 : (HD > 256 ? 2 : 3);  // 32 KB V stages
   static constexpr int kBudget = kSmemLimit - 3072;  // static smem (barriers + exchange), 1 KB aligned
   static constexpr int kNksRaw = (kBudget - Q_BYTES - P_BYTES - NVS * 32768) / 16384;
   static constexpr int NKS = kNksRaw > 8 ? 8 : kNksRaw;   // 16 KB K stages
   static constexpr int SMEM_DYN = Q_BYTES + P_BYTES + NKS * 16384 + NVS * 32768;
   static_assert(NKS >= 2, "not enough shared memory for the K ring");
-  static_assert(O_COLS <= 256, "O does not fit TMEM next to S");
-  __host__ __device__ static constexpr int slice_n(int s) { return (DVP - 256 * s) >= 256 ? 256 : 128; }
+  static_assert(O_COLS + 128 <= 512 && S_BASE >= O_COLS, "O does not fit TMEM next to S");
+  // width of the O slab of pass `pass`, and N of its slice s
+  __host__ __device__ static constexpr int slab_w(int pass) { return (DVP - pass * DSLAB) >= DSLAB ? DSLAB : (DVP - pass * DSLAB); }
+  __host__ __device__ static constexpr int slice_n(int w, int s) { return (w - 256 * s) >= 256 ? 256 : 128; }
 };
 
 struct Barriers {
@@ -172,11 +178,13 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t l_q_full = ptx::mapa(bar(bars.q_full), 0);
       for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters, ++it) {
         const int mt = item % p.n_mtiles;
-        const int bh = item / p.n_mtiles;
+        const int pass = (item / p.n_mtiles) % Cfg::NPASS;
+        const int bh = item / (p.n_mtiles * Cfg::NPASS);
         const int h = bh % p.heads_q, b = bh / p.heads_q;
         const int hk = h / group;
         const int q0 = mt * 128;
         const int T = num_kv_tiles(p, q0);
+        const int dv0 = pass * Cfg::DSLAB, dvw = Cfg::slab_w(pass);
         ptx::mbar_wait(bar(bars.q_empty), (it & 1) ^ 1);
         if (rank == 0) ptx::mbar_expect_tx(bar(bars.q_full), 2 * Cfg::Q_BYTES);
 #pragma unroll
@@ -202,15 +210,16 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const int kv0 = (step - 1) * 128;
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
+              if (256 * s >= dvw) break;
               const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
               ptx::mbar_wait(bar(bars.v_empty[stage]), (n & 1) ^ 1);
-              const int ns = Cfg::slice_n(s);
+              const int ns = Cfg::slice_n(dvw, s);
               const int nb = ns / 128;  // 64-wide boxes this CTA loads
               if (rank == 0) ptx::mbar_expect_tx(bar(bars.v_full[stage]), 2 * nb * 16384);
               const uint32_t l_full = ptx::mapa(bar(bars.v_full[stage]), 0);
               for (int bx = 0; bx < nb; ++bx)
                 ptx::tma_load_4d_2sm(sV + stage * 32768 + bx * 16384, &map_v, l_full,
-                                     256 * s + (ns / 2) * (int)rank + 64 * bx, kv0, hk, b);
+                                     dv0 + 256 * s + (ns / 2) * (int)rank + 64 * bx, kv0, hk, b);
               ++vc;
             }
           }
@@ -226,6 +235,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       uint32_t kc = 0, vc = 0, it = 0, g = 0, gp = 0;
       for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters, ++it) {
         const int mt = item % p.n_mtiles;
+        const int pass = (item / p.n_mtiles) % Cfg::NPASS;
+        const int dvw = Cfg::slab_w(pass);
         const int T = num_kv_tiles(p, mt * 128);
         ptx::mbar_wait(bar(bars.q_full), it & 1);
         ptx::tc_fence_after();
@@ -260,10 +271,11 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             ptx::tc_fence_after();
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
+              if (256 * s >= dvw) break;
               const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
               ptx::mbar_wait(bar(bars.v_full[stage]), n & 1);
               ptx::tc_fence_after();
-              const int ns = Cfg::slice_n(s);
+              const int ns = Cfg::slice_n(dvw, s);
               const uint32_t idesc_pv = ptx::make_idesc(fmt, fmt, 0, 1, 128, ns);
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk) {
@@ -300,10 +312,12 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint32_t g = 0;
     for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
       const int mt = item % p.n_mtiles;
-      const int bh = item / p.n_mtiles;
+      const int pass = (item / p.n_mtiles) % Cfg::NPASS;
+      const int bh = item / (p.n_mtiles * Cfg::NPASS);
       const int h = bh % p.heads_q, b = bh / p.heads_q;
       const int q0 = mt * 128;
       const int T = num_kv_tiles(p, q0);
+      const int dv0 = pass * Cfg::DSLAB, dvw = Cfg::slab_w(pass);
       const int gq = q0 + 64 * (int)rank + (int)row;  // global query row of this thread
       const int causal_lim = gq + (p.seqlen_kv - p.seqlen_q);  // last visible key when causal
       float m = NEG_INF, l = 0.f;
@@ -433,7 +447,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           ptx::mbar_wait(bar(bars.p_empty[(g - 1) & 1]), ((g - 1) >> 1) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int c0 = (int)ch * (Cfg::O_COLS / 2); c0 < (int)(ch + 1) * (Cfg::O_COLS / 2); c0 += 32) {
+          for (int c0 = (int)ch * (dvw / 4); c0 < (int)(ch + 1) * (dvw / 4); c0 += 32) {
             uint32_t orr[32];
             ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
             ptx::tmem_wait_ld();
@@ -466,14 +480,15 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         2 * ((int64_t)b * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)gq * p.o_stride[2]);
 #pragma unroll
         for (int s = 0; s < Cfg::NSLICE; ++s) {
-          const int ns = Cfg::slice_n(s);
+          if (256 * s >= dvw) break;
+          const int ns = Cfg::slice_n(dvw, s);
           const int half = ns / 4;  // columns of this slice handled by each warpgroup
 #pragma unroll 1
           for (int c0 = (int)ch * half; c0 < (int)(ch + 1) * half; c0 += 32) {
             uint32_t orr[32];
             ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
             ptx::tmem_wait_ld();
-            const int d0 = 256 * s + (ns / 2) * (int)kh + c0;
+            const int d0 = dv0 + 256 * s + (ns / 2) * (int)kh + c0;
             if (row_ok) {
 #pragma unroll
               for (int v = 0; v < 4; ++v) {
@@ -492,7 +507,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
         }
-        if (p.lse != nullptr && slot == 0 && row_ok) {
+        if (p.lse != nullptr && slot == 0 && row_ok && pass == 0) {
           // natural-log LSE; rows without any visible key: O = 0, LSE = -inf
           const float lse = (l_tot > 0.f) ? (m * mul + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
           p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
@@ -540,7 +555,15 @@ static int dispatch_nqk(int nqk, const CUtensorMap& mq, const CUtensorMap& mk, c
     case 6: return launch_variant<6, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
     case 7: return launch_variant<7, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
     case 8: return launch_variant<8, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    default: return set_error(FFPA_ERR_UNSUPPORTED, "head_dim > 512 not supported by this kernel");
+    case 9: return launch_variant<9, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 10: return launch_variant<10, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 11: return launch_variant<11, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 12: return launch_variant<12, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 13: return launch_variant<13, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 14: return launch_variant<14, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 15: return launch_variant<15, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 16: return launch_variant<16, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    default: return set_error(FFPA_ERR_UNSUPPORTED, "head_dim > 1024 not supported");
   }
 }
 

@@ -21,6 +21,22 @@ struct FwdKernelParams {
   int n_mtiles, n_items;
 };
 
+namespace bwd {
+// kernel-side parameters of the backward kernels (tensor maps carry the operands)
+struct BwdKernelParams {
+  void* out;               // dQ / dK / dV
+  int64_t out_stride[3];   // (b, h, n) elements
+  const float* lse2;       // [B, Hq, Nq_pad]  LSE * log2(e); +inf for rows without keys / padding
+  const float* delta;      // [B, Hq, Nq_pad]  rowsum(dO * O); 0 in the padding
+  int nq_pad;
+  int batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
+  int causal;
+  float scale_log2;        // softmax_scale * log2(e)
+  float scale;             // softmax_scale
+  int n_rtiles, n_items;   // row tiles (128 stationary rows) per (b, head); total items
+};
+}  // namespace bwd
+
 int set_error(int code, const char* fmt, ...);
 void count_launch();
 int sm_count();

@@ -122,6 +122,13 @@ int main(int argc, char** argv) {
       {1, 32, 32, 8192, 8192, 320, 0, 1, 10},
       {1, 32, 32, 8192, 8192, 256, 0, 1, 10},
       {1, 32, 32, 8192, 8192, 128, 0, 1, 10},
+      {1, 2, 2, 512, 512, 768, 0, 1, 0},
+      {1, 2, 2, 300, 400, 1024, 1, 1, 0},
+      {1, 2, 2, 512, 512, 640, 0, 0, 0},
+      {1, 2, 2, 260, 512, 896, 0, 1, 0},
+      {1, 32, 32, 8192, 8192, 768, 0, 1, 5},
+      {1, 32, 32, 8192, 8192, 1024, 0, 1, 5},
+      {1, 32, 8, 4096, 4096, 512, 1, 1, 10},
   };
   int only = argc > 1 ? atoi(argv[1]) : -1;
   int fails = 0;
