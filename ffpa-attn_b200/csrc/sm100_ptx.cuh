@@ -74,10 +74,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on a barrier that lives in another CTA of the cluster (address from mapa)
+// arrive on a barrier that lives in another CTA of the cluster (address from mapa).
+// Default (.release.cta) semantics on purpose: `.release.cluster` compiles to
+// MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, which ncu showed as ~40 % of the softmax warps' stall
+// samples (profiles/r01_fwd_d512_v2_ncu.md). The data being published is this CTA's own shared
+// memory, made visible to the async proxy by fence.proxy.async before the arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -90,12 +93,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// cluster-scope acquire: pairs with mbar_arrive_cluster from the peer CTA
+// wait on a barrier that peer-CTA threads arrive on (same instruction as mbar_try_wait; kept as a
+// separate name to mark the cross-CTA hand-offs)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
