@@ -316,6 +316,8 @@ class _FFPAAttnFunc(torch.autograd.Function):
     if ctx.attn_bias is not None or meta.attn_meta.dropout_p > 0.0:
       raise NotImplementedError(
         "ffpa_attn backward with attn_mask / dropout is not implemented by the sm_100a kernels yet")
+    if q.size(-1) > 512:
+      raise NotImplementedError("ffpa_attn backward supports head_dim <= 512 on sm_100a (TMEM capacity)")
     dq, dk, dv = _ffpa_attn_backward_cuda(
       q, k, v, O, lse, d_o.contiguous(), meta.backward_meta.stages, int(meta.attn_meta.is_causal),
       meta.attn_meta.scale)

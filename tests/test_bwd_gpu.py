@@ -1,0 +1,158 @@
+"""GPU parity tests for the backward (dQ, dK, dV) through the public API / autograd ->
+torch.ops.ffpa_attn._bwd_cuda -> C ABI -> sm_100a kernels. Oracle: oracle/attention_oracle.py
+(pinned on the reference's own autograd results in tests/golden/*_bwd.npz); full-size configs use a
+plain fp32 torch restatement on the GPU. Tolerances follow the reference's backward tests
+(/root/reference/tests/test_ffpa_bwd.py:38-45, 975-985): fp16 1e-2, bf16 5e-2, causal bf16 large 1e-1;
+and its analytic KATs (/root/reference/tests/test_ffpa_cute_sm100.py:1026-1050)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _tol(dtype):
+  return 5e-2 if dtype == torch.bfloat16 else 1e-2
+
+
+def _grads(q, k, v, d_o, **kw):
+  import ffpa_attn
+
+  q, k, v = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+  n0 = ffpa_attn._C.launch_count()
+  out = ffpa_attn.ffpa_attn_func(q, k, v, **kw)
+  out.backward(d_o)
+  torch.cuda.synchronize()
+  assert ffpa_attn._C.launch_count() - n0 >= 5, "expected fwd + preprocess + dQ + dK + dV launches"
+  return out.detach(), q.grad, k.grad, v.grad
+
+
+def _mk(B, Hq, Hkv, Nq, Nkv, D, dtype, seed=0):
+  torch.manual_seed(seed)
+  q = torch.randn(B, Hq, Nq, D).to(dtype).to(DEV)
+  k = torch.randn(B, Hkv, Nkv, D).to(dtype).to(DEV)
+  v = torch.randn(B, Hkv, Nkv, D).to(dtype).to(DEV)
+  d_o = torch.randn(B, Hq, Nq, D).to(dtype).to(DEV)
+  return q, k, v, d_o
+
+
+def _cmp(got, want, tol, name):
+  g = got.float().cpu().numpy()
+  assert np.isfinite(g).all(), f"{name}: non-finite gradient"
+  err = np.abs(g - want).max()
+  bound = tol * max(1.0, float(np.abs(want).max()))
+  assert err < bound, f"{name}: max-abs-err {err:.3e} >= {bound:.3e}"
+
+
+def _check_against_oracle(q, k, v, d_o, causal, dtype, enable_gqa=False, tol=None):
+  _, dq, dk, dv = _grads(q, k, v, d_o, is_causal=causal, enable_gqa=enable_gqa)
+  rq, rk, rv, _ = orc.attention_bwd(q.cpu(), k.cpu(), v.cpu(), d_o.cpu(), causal=causal)
+  tol = tol or _tol(dtype)
+  _cmp(dq, rq, tol, "dQ")
+  _cmp(dk, rk, tol, "dK")
+  _cmp(dv, rv, tol, "dV")
+
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*_bwd.npz")))
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "mask" not in p],
+                         ids=[os.path.basename(p)[:-4] for p in GOLDEN if "mask" not in p])
+def test_backward_matches_reference_golden(path):
+  z = np.load(path)
+  B, Hq, Hkv, Nq, Nkv, D, is_bf16, causal = [int(x) for x in z["meta"]]
+  dt = torch.bfloat16 if is_bf16 else torch.float16
+  t = lambda n, s: torch.from_numpy(z[n].view(np.int16).copy()).view(dt).reshape(s).to(DEV)  # noqa: E731
+  q, k, v = t("q", (B, Hq, Nq, D)), t("k", (B, Hkv, Nkv, D)), t("v", (B, Hkv, Nkv, D))
+  d_o = t("d_o", (B, Hq, Nq, D))
+  _, dq, dk, dv = _grads(q, k, v, d_o, is_causal=bool(causal), enable_gqa=Hq != Hkv)
+  for got, name in ((dq, "dq"), (dk, "dk"), (dv, "dv")):
+    _cmp(got, z[name].astype(np.float64), _tol(dt), name)
+
+
+@pytest.mark.parametrize("D", [64, 128, 256, 320, 512])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_backward_headdims(D, dtype):
+  q, k, v, d_o = _mk(1, 2, 2, 256, 256, D, dtype)
+  _check_against_oracle(q, k, v, d_o, False, dtype)
+
+
+@pytest.mark.parametrize("Nq,Nkv", [(128, 128), (130, 257), (1, 300), (7, 129), (384, 200), (500, 1000)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_backward_shapes_and_tails(Nq, Nkv, causal):
+  if causal and Nkv < Nq:
+    pytest.skip("causal needs Nkv >= Nq")
+  q, k, v, d_o = _mk(2, 2, 2, Nq, Nkv, 320, torch.float16, seed=1)
+  _check_against_oracle(q, k, v, d_o, causal, torch.float16)
+
+
+@pytest.mark.parametrize("Hq,Hkv", [(4, 2), (8, 1), (6, 3)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_backward_gqa(Hq, Hkv, causal):  # tests/test_ffpa_bwd.py:991-997
+  q, k, v, d_o = _mk(1, Hq, Hkv, 256, 384, 512, torch.bfloat16, seed=2)
+  _check_against_oracle(q, k, v, d_o, causal, torch.bfloat16, enable_gqa=True, tol=1e-1 if causal else None)
+
+
+def test_backward_single_key_kat():
+  """s_k == 1: softmax is identically 1 -> dQ = dK = 0 exactly-ish, dV = sum over rows of dO."""
+  q, k, v, d_o = _mk(1, 2, 2, 200, 1, 128, torch.bfloat16, seed=3)
+  _, dq, dk, dv = _grads(q, k, v, d_o)
+  assert dq.float().abs().max().item() < 1e-2
+  assert dk.float().abs().max().item() < 5e-2
+  want = d_o.float().sum(dim=2, keepdim=True)
+  assert (dv.float() - want).abs().max().item() < 5e-2 * max(1.0, want.abs().max().item())
+
+
+def test_backward_linear_in_dO():
+  """Size-independent property: gradients are linear in dO."""
+  q, k, v, d_o = _mk(1, 2, 2, 300, 300, 256, torch.float16, seed=4)
+  _, a_q, a_k, a_v = _grads(q, k, v, d_o)
+  _, b_q, b_k, b_v = _grads(q, k, v, 2 * d_o)
+  for a, b in ((a_q, b_q), (a_k, b_k), (a_v, b_v)):
+    assert (2 * a.float() - b.float()).abs().max().item() < 2e-2 * max(1.0, b.float().abs().max().item())
+
+
+def _torch_ref_grads(q, k, v, d_o, causal):
+  q32, k32, v32 = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+  g = q.size(1) // k.size(1)
+  kk, vv = k32.repeat_interleave(g, dim=1), v32.repeat_interleave(g, dim=1)
+  s = (q32 @ kk.transpose(-1, -2)) * q.size(-1) ** -0.5
+  if causal:
+    Nq, Nkv = q.size(2), k.size(2)
+    m = torch.arange(Nkv, device=q.device)[None, :] <= (torch.arange(Nq, device=q.device)[:, None] + (Nkv - Nq))
+    s = s.masked_fill(~m, float("-inf"))
+  o = torch.softmax(s, dim=-1) @ vv
+  o.backward(d_o.float())
+  return q32.grad, k32.grad, v32.grad
+
+
+def test_c3_full_size_gqa_causal_backward():
+  """BASELINE config 3: Hq=32 Hkv=8 N=4096 D=512 causal bf16, forward + backward. Reference grads in
+  fp32 torch on the GPU for two KV heads (8 query heads)."""
+  q, k, v, d_o = _mk(1, 32, 8, 4096, 4096, 512, torch.bfloat16, seed=42)
+  _, dq, dk, dv = _grads(q, k, v, d_o, is_causal=True, enable_gqa=True)
+  for hk in (0, 7):
+    hs = slice(4 * hk, 4 * hk + 4)
+    rq, rk, rv = _torch_ref_grads(q[:, hs], k[:, hk:hk + 1], v[:, hk:hk + 1], d_o[:, hs], True)
+    for got, want, name in ((dq[:, hs], rq, "dQ"), (dk[:, hk:hk + 1], rk, "dK"), (dv[:, hk:hk + 1], rv, "dV")):
+      err = (got.float() - want).abs().max().item()
+      bound = 1e-1 * max(1.0, want.abs().max().item())  # tests/test_ffpa_bwd.py:975-985 (causal bf16, D>=512)
+      assert err < bound, f"{name} kv-head {hk}: {err:.3e} >= {bound:.3e}"
+      cos = torch.nn.functional.cosine_similarity(got.float().flatten(), want.flatten(), dim=0).item()
+      assert cos > 0.999, f"{name} kv-head {hk}: cosine {cos}"  # tests/test_ffpa_cute_sm100.py:822-842
+
+
+def test_backward_rejects_unsupported():
+  import ffpa_attn
+
+  q, k, v, d_o = _mk(1, 2, 2, 128, 128, 768, torch.bfloat16)
+  q.requires_grad_(True)
+  out = ffpa_attn.ffpa_attn_func(q, k, v)
+  with pytest.raises(NotImplementedError):
+    out.backward(d_o)
