@@ -1,0 +1,77 @@
+"""Secondary timings (CUDA events, device-resident inputs): forward / backward TFLOPS for the
+BASELINE.json configs other than the headline one. Prints one JSON line per case."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "ffpa-attn_b200"))
+import torch  # noqa: E402
+
+import ffpa_attn  # noqa: E402
+
+CASES = [
+  # name, B, Hq, Hkv, Nq, Nkv, D, causal
+  ("c2_self_d512", 1, 32, 32, 8192, 8192, 512, False),
+  ("c2_causal_d512", 1, 32, 32, 8192, 8192, 512, True),
+  ("gqa_d512", 1, 32, 8, 8192, 8192, 512, False),
+  ("c3_gqa_causal_n4096_d512", 1, 32, 8, 4096, 4096, 512, True),
+  ("cross_nq1024_d512", 1, 32, 32, 1024, 8192, 512, False),
+  ("nonaligned_n8191_h8_d512", 1, 8, 8, 8191, 8191, 512, False),
+  ("self_n16384_d512", 1, 32, 32, 16384, 16384, 512, False),
+  ("d320", 1, 32, 32, 8192, 8192, 320, False),
+  ("d256", 1, 32, 32, 8192, 8192, 256, False),
+  ("d128", 1, 32, 32, 8192, 8192, 128, False),
+  ("d768", 1, 32, 32, 8192, 8192, 768, False),
+  ("d1024", 1, 32, 32, 8192, 8192, 1024, False),
+]
+
+
+def flops(B, Hq, Nq, Nkv, D, causal):
+  pairs = (Nq * (Nkv - Nq) + Nq * (Nq + 1) // 2) if causal else Nq * Nkv
+  return 4.0 * B * Hq * D * pairs
+
+
+def timeit(fn, iters):
+  for _ in range(3):
+    fn()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(iters):
+    fn()
+  e1.record()
+  torch.cuda.synchronize()
+  return e0.elapsed_time(e1) / iters
+
+
+def main():
+  only = sys.argv[1:] or None
+  dev = "cuda"
+  for name, B, Hq, Hkv, Nq, Nkv, D, causal in CASES:
+    if only and name not in only:
+      continue
+    torch.manual_seed(42)
+    q = torch.randn(B, Hq, Nq, D, dtype=torch.bfloat16, device=dev)
+    k = torch.randn(B, Hkv, Nkv, D, dtype=torch.bfloat16, device=dev)
+    v = torch.randn(B, Hkv, Nkv, D, dtype=torch.bfloat16, device=dev)
+    kw = dict(is_causal=causal, enable_gqa=Hq != Hkv)
+    f = flops(B, Hq, Nq, Nkv, D, causal)
+    ms_f = timeit(lambda: ffpa_attn.ffpa_attn_func(q, k, v, **kw), 10)
+    rec = {"case": name, "fwd_ms": ms_f, "fwd_tflops": f / ms_f * 1e-9}
+    if D <= 512:
+      qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+      out = ffpa_attn.ffpa_attn_func(qg, kg, vg, **kw)
+      d_o = torch.randn_like(out)
+
+      def bwd():
+        out.backward(d_o, retain_graph=True)
+
+      ms_b = timeit(bwd, 5)
+      rec.update({"bwd_ms": ms_b, "bwd_tflops": 2.5 * f / ms_b * 1e-9})
+    print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+  main()
