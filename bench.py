@@ -354,6 +354,37 @@ def main():
               "algorithmic_hbm_bytes_per_launch": int(2 * (2 * q.numel() + k.numel() + v.numel())),
               "launch_ms_mean": mean_launch_ms, "launch_ms_min": min(per_launch_ms)}
 
+  # ---- secondary numbers of the same metric family (BASELINE.json: "attn TFLOPS (fwd, bwd)") ----
+  also = None
+  if world == 1 and not args.no_e2e:
+    also = {}
+    def _t(fn, n):
+      for _ in range(2):
+        fn()
+      torch.cuda.synchronize()
+      a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      for _ in range(n):
+        fn()
+      b_.record()
+      torch.cuda.synchronize()
+      return a.elapsed_time(b_) / n
+    for name in (args.workload, "c3_gqa_causal_fwd_hq32hkv8n4096d512"):
+      b2, hq2, hkv2, nq2, nkv2, d2, c2 = WORKLOADS[name]
+      torch.manual_seed(7)
+      qg = torch.randn(b2, hq2, nq2, d2, dtype=dt, device=dev, requires_grad=True)
+      kg = torch.randn(b2, hkv2, nkv2, d2, dtype=dt, device=dev, requires_grad=True)
+      vg = torch.randn(b2, hkv2, nkv2, d2, dtype=dt, device=dev, requires_grad=True)
+      kw2 = dict(is_causal=c2, enable_gqa=hq2 != hkv2)
+      f2 = flops_of(b2, hq2, nq2, nkv2, d2, c2)
+      ms_f = _t(lambda: ffpa_attn.ffpa_attn_func(qg.detach(), kg.detach(), vg.detach(), **kw2), 10)
+      o2 = ffpa_attn.ffpa_attn_func(qg, kg, vg, **kw2)
+      do2 = torch.randn_like(o2)
+      ms_b = _t(lambda: o2.backward(do2, retain_graph=True), 5)
+      also[name] = {"fwd_ms": ms_f, "fwd_tflops": f2 / ms_f * 1e-9, "bwd_ms": ms_b,
+                    "bwd_tflops": 2.5 * f2 / ms_b * 1e-9, "bwd_flops_rule": "2.5 x fwd (reference _flops.py:57-76)"}
+      del qg, kg, vg, o2, do2
+
   # ---- CPU baseline on this box's host cores (bounded sample) ----
   cpu = None
   if not args.no_cpu_baseline:
@@ -368,7 +399,7 @@ def main():
     "vs_baseline": (value / world / 1456.0) if args.workload == DEFAULT_WORKLOAD else None,
     "dtype": "bf16", "data": "synthetic", "config": config, "roofline": roofline,
     "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
-    "max_abs_err_vs_oracle": max_abs_err,
+    "max_abs_err_vs_oracle": max_abs_err, "also": also,
     "reference_published": {"value": 1456.0, "unit": "TFLOP/s", "where": "bench/README.md:132 (CuTe-DSL tcgen05, B200)",
                             "ratio": value / world / 1456.0 if args.workload == DEFAULT_WORKLOAD else None},
   }
