@@ -100,9 +100,16 @@ int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream) {
   if (int e = check_strides("O", p->o_stride, qd)) return e;
   if (!aligned16(p->q) || !aligned16(p->k) || !aligned16(p->v) || !aligned16(p->o))
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "q/k/v/o base pointers must be 16-byte aligned");
-  if (p->fp8 || g_impl_hint.load() == FFPA_IMPL_CUTE_TMA_FP4)
-    return set_error(FFPA_ERR_UNSUPPORTED, p->fp8 ? "FP8 forward is not built into this library yet" : "FP4 path is not implemented on sm_100a");
+  if (g_impl_hint.load() == FFPA_IMPL_CUTE_TMA_FP4)
+    return set_error(FFPA_ERR_UNSUPPORTED, "FP4 path is not implemented on sm_100a");
+  if (p->fp8) return launch_fwd_fp8_sm100(*p, static_cast<cudaStream_t>(stream));
   return launch_fwd_sm100(*p, static_cast<cudaStream_t>(stream));
+}
+
+uint64_t ffpa_b200_fwd_workspace_bytes(int32_t batch, int32_t heads_q, int32_t heads_kv, int32_t seqlen_q,
+                                       int32_t seqlen_kv, int32_t head_dim, int32_t fp8) {
+  if (!fp8) return 0;
+  return fwd_fp8_workspace_bytes(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
 }
 
 int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream) {

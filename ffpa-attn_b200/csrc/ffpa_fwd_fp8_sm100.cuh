@@ -1,0 +1,527 @@
+// B200 (sm_100a) FP8 attention forward: tcgen05.mma kind::f8f6f4 (e4m3 x e4m3 -> fp32 TMEM).
+//
+// Semantics follow the reference's FP8 path (per-block scales, P quantised with the V scale folded
+// in; /root/reference/csrc/cuffpa/cute/fp8/quantize_fp8.cuh:56-168, fp8_pscale.cuh:11-76,
+// cute/fp8/sm_120/split_d.cuh:26-43) re-designed for sm_100a:
+//   Q8 = e4m3(Q / qs), qs = amax(128-row block) / 448     (same for K8/ks, V8/vs)
+//   S  = (Q8 K8^T) * qs * ks[tile] * scale                 -> online softmax (lazy threshold 4.0)
+//   P8 = e4m3(P * (vs[tile] / vref) * 28),  vref = max_tile vs,  28 = 448 / 2^4 (lazy-rescale slack)
+//   O  = (sum_tiles P8 V8) * vref / 28 / l
+// One fused pre-pass (quantize_e4m3_kernel) writes Q8/K8/V8 + scales once; the attention kernel
+// streams 1-byte tiles (half the L2->SMEM bytes of the bf16 kernel). V stays row-major [keys x d]
+// and is consumed as an MN-major B operand (the reference pre-transposes V for its mma.sync path).
+// Kernel structure (2-CTA cluster, lane-folded TMEM accumulators, warp roles, mbarrier pipelines)
+// is the one of ffpa_fwd_sm100.cuh; byte geometry of the tiles is identical (128-byte swizzled
+// rows), only the element count per row doubles (128 e4m3 per row, MMA K = 32).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cmath>
+#include "ffpa_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace ffpa {
+namespace fp8 {
+
+constexpr int kSoftmaxWarps = 8;
+constexpr int kMmaWarp = 8;
+constexpr int kTmaWarp = 9;
+constexpr int kThreads = 320;
+constexpr int kSmemLimit = 232448;
+constexpr float kLazyThreshold = 4.0f;   // /root/reference/csrc/cuffpa/common.cuh:14-18 (fp8)
+constexpr float kPScale = 28.0f;         // 448 / 2^kLazyThreshold
+
+struct Fp8KernelParams {
+  void* o;
+  float* lse;
+  int64_t o_stride[3];
+  const float* qs;     // [B, Hq,  TQ]
+  const float* ks;     // [B, Hkv, TK]
+  const float* vs;     // [B, Hkv, TK]
+  const float* vref;   // [B, Hkv]
+  int tq, tk;
+  int batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
+  int causal;
+  float scale_log2;
+  int n_mtiles, n_items;
+};
+
+template <int NB>  // number of 128-wide head-dim boxes (head_dim padded to NB*128)
+struct Fp8Cfg {
+  static constexpr int HD = NB * 128;
+  static constexpr int DVP = ((HD + 255) / 256) * 256;
+  static constexpr int NSLICE = DVP / 256;
+  static constexpr int O_COLS = DVP / 2;
+  static constexpr int KST = (NB + 1) / 2;         // 16 KB K stages ([64 keys x 256 d]) per KV tile
+  static constexpr int S_BASE = 256;
+  static constexpr int Q_BYTES = NB * 8192;
+  static constexpr int P_BYTES = 2 * 8192;
+  static constexpr int kBudget = kSmemLimit - 3072;
+  static constexpr int kAvail = (kBudget - Q_BYTES - P_BYTES) / 16384;
+  static constexpr int NVS = (kAvail / 2) > 6 ? 6 : (kAvail / 2);    // 16 KB V stages ([128 keys x 128 d])
+  static constexpr int NKS = (kAvail - NVS) > 8 ? 8 : (kAvail - NVS);
+  static constexpr int SMEM_DYN = Q_BYTES + P_BYTES + (NKS + NVS) * 16384;
+  static_assert(O_COLS <= 256, "fp8 kernel supports head_dim <= 512");
+  static_assert(NKS >= 2 && NVS >= 2, "not enough shared memory");
+};
+
+struct Barriers {
+  uint64_t q_full, q_empty;
+  uint64_t k_full[8], k_empty[8];
+  uint64_t v_full[6], v_empty[6];
+  uint64_t s_full[2];
+  uint64_t p_full[2], p_empty[2];
+};
+
+__device__ __forceinline__ int num_kv_tiles(const Fp8KernelParams& p, int q0) {
+  int tc = (p.seqlen_kv + 127) >> 7;
+  if (p.causal) {
+    int lim = ((q0 + 127 + (p.seqlen_kv - p.seqlen_q)) >> 7) + 1;
+    tc = lim < tc ? lim : tc;
+  }
+  return tc < 1 ? 1 : tc;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// two floats -> two e4m3 bytes (lo at the lower address)
+__device__ __forceinline__ uint32_t pack_e4m3x2(float lo, float hi) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  return pack_e4m3x2(a, b) | (pack_e4m3x2(c, d) << 16);
+}
+
+template <int NB, bool OUT_BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const Fp8KernelParams p) {
+  using Cfg = Fp8Cfg<NB>;
+  constexpr int CG = 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ Barriers bars;
+  __shared__ float xch[2][4][64];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  const uint32_t sQ = smem_base;
+  const uint32_t sP = sQ + Cfg::Q_BYTES;
+  const uint32_t sK = sP + Cfg::P_BYTES;
+  const uint32_t sV = sK + Cfg::NKS * 16384;
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t cluster = blockIdx.x >> 1;
+  const uint32_t nclusters = gridDim.x >> 1;
+  auto bar = [](uint64_t& b) { return ptx::smem_u32(&b); };
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar(bars.q_full), 1);
+    ptx::mbar_init(bar(bars.q_empty), 1);
+    for (int i = 0; i < 8; ++i) { ptx::mbar_init(bar(bars.k_full[i]), 1); ptx::mbar_init(bar(bars.k_empty[i]), 1); }
+    for (int i = 0; i < 6; ++i) { ptx::mbar_init(bar(bars.v_full[i]), 1); ptx::mbar_init(bar(bars.v_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar(bars.s_full[i]), 1);
+      ptx::mbar_init(bar(bars.p_full[i]), 2 * kSoftmaxWarps);
+      ptx::mbar_init(bar(bars.p_empty[i]), 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == kTmaWarp && ptx::elect_one()) {
+    ptx::prefetch_tmap(&map_q);
+    ptx::prefetch_tmap(&map_k);
+    ptx::prefetch_tmap(&map_v);
+  }
+  if (warp == kMmaWarp) {
+    ptx::tmem_alloc<CG>(ptx::smem_u32(&tmem_slot), 512);
+    ptx::tmem_relinquish<CG>();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int group = p.heads_q / p.heads_kv;
+
+  if (warp == kTmaWarp) {
+    // =========================================== TMA producer ===================================
+    if (ptx::elect_one()) {
+      uint32_t kc = 0, vc = 0, it = 0;
+      const uint32_t l_q_full = ptx::mapa(bar(bars.q_full), 0);
+      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters, ++it) {
+        const int mt = item % p.n_mtiles;
+        const int bh = item / p.n_mtiles;
+        const int h = bh % p.heads_q, b = bh / p.heads_q;
+        const int hk = h / group;
+        const int q0 = mt * 128;
+        const int T = num_kv_tiles(p, q0);
+        ptx::mbar_wait(bar(bars.q_empty), (it & 1) ^ 1);
+        if (rank == 0) ptx::mbar_expect_tx(bar(bars.q_full), 2 * Cfg::Q_BYTES);
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb)
+          ptx::tma_load_4d_2sm(sQ + jb * 8192, &map_q, l_q_full, jb * 128, q0 + 64 * (int)rank, h, b);
+        for (int step = 0; step <= T; ++step) {
+          if (step < T) {
+            const int kv0 = step * 128;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KST; ++ks) {
+              const uint32_t stage = kc % Cfg::NKS, n = kc / Cfg::NKS;
+              ptx::mbar_wait(bar(bars.k_empty[stage]), (n & 1) ^ 1);
+              const int nb = (NB - 2 * ks) >= 2 ? 2 : 1;
+              if (rank == 0) ptx::mbar_expect_tx(bar(bars.k_full[stage]), 2 * nb * 8192);
+              const uint32_t l_full = ptx::mapa(bar(bars.k_full[stage]), 0);
+              for (int bx = 0; bx < nb; ++bx)
+                ptx::tma_load_4d_2sm(sK + stage * 16384 + bx * 8192, &map_k, l_full, (2 * ks + bx) * 128,
+                                     kv0 + 64 * (int)rank, hk, b);
+              ++kc;
+            }
+          }
+          if (step >= 1) {
+            const int kv0 = (step - 1) * 128;
+#pragma unroll
+            for (int s = 0; s < Cfg::NSLICE; ++s) {
+              const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
+              ptx::mbar_wait(bar(bars.v_empty[stage]), (n & 1) ^ 1);
+              if (rank == 0) ptx::mbar_expect_tx(bar(bars.v_full[stage]), 2 * 16384);
+              const uint32_t l_full = ptx::mapa(bar(bars.v_full[stage]), 0);
+              ptx::tma_load_4d_2sm(sV + stage * 16384, &map_v, l_full, 256 * s + 128 * (int)rank, kv0, hk, b);
+              ++vc;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // =========================================== MMA issuer (leader CTA) ========================
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc_qk = ptx::make_idesc(0, 0, 0, 0, 128, 128);   // e4m3 x e4m3, K-major both
+      constexpr uint32_t idesc_pv = ptx::make_idesc(0, 0, 0, 1, 128, 256);   // B = V, MN-major
+      uint32_t kc = 0, vc = 0, it = 0, g = 0, gp = 0;
+      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters, ++it) {
+        const int mt = item % p.n_mtiles;
+        const int T = num_kv_tiles(p, mt * 128);
+        ptx::mbar_wait(bar(bars.q_full), it & 1);
+        ptx::tc_fence_after();
+        for (int step = 0; step <= T; ++step) {
+          if (step < T) {
+            const uint32_t sbuf = g & 1;
+            const uint32_t d_tmem = tmem + Cfg::S_BASE + 64 * sbuf;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KST; ++ks) {
+              const uint32_t stage = kc % Cfg::NKS, n = kc / Cfg::NKS;
+              ptx::mbar_wait(bar(bars.k_full[stage]), n & 1);
+              ptx::tc_fence_after();
+              const int nb = (NB - 2 * ks) >= 2 ? 2 : 1;
+              for (int bx = 0; bx < nb; ++bx) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {  // 32 e4m3 = 32 bytes per MMA K step
+                  const uint64_t ad = ptx::make_smem_desc_sw128(sQ + (2 * ks + bx) * 8192 + k4 * 32, 16, 1024);
+                  const uint64_t bd = ptx::make_smem_desc_sw128(sK + stage * 16384 + bx * 8192 + k4 * 32, 16, 1024);
+                  ptx::umma_f8_ss<CG>(d_tmem, ad, bd, idesc_qk, (ks | bx | k4) != 0 ? 1u : 0u);
+                }
+              }
+              ptx::umma_commit_mc<CG>(bar(bars.k_empty[stage]), 0x3);
+              ++kc;
+            }
+            ptx::umma_commit_mc<CG>(bar(bars.s_full[sbuf]), 0x3);
+            if (step == T - 1) ptx::umma_commit_mc<CG>(bar(bars.q_empty), 0x3);
+            ++g;
+          }
+          if (step >= 1) {
+            const uint32_t pbuf = gp & 1;
+            ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp >> 1) & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < Cfg::NSLICE; ++s) {
+              const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
+              ptx::mbar_wait(bar(bars.v_full[stage]), n & 1);
+              ptx::tc_fence_after();
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {  // 32 keys per MMA: 4 atoms of 8 key-lines
+                const uint64_t ad = ptx::make_smem_desc_sw128(sP + pbuf * 8192 + kk * 32, 16, 1024);
+                const uint64_t bd = ptx::make_smem_desc_sw128(sV + stage * 16384 + kk * 4096, 16384, 1024);
+                ptx::umma_f8_ss<CG>(tmem + 128 * s, ad, bd, idesc_pv, (step > 1 || kk > 0) ? 1u : 0u);
+              }
+              ptx::umma_commit_mc<CG>(bar(bars.v_empty[stage]), 0x3);
+              ++vc;
+            }
+            ptx::umma_commit_mc<CG>(bar(bars.p_empty[pbuf]), 0x3);
+            ++gp;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================== softmax / correction / epilogue ================
+    const uint32_t t = threadIdx.x;
+    const uint32_t lane128 = t & 127;
+    const uint32_t row = lane128 & 63;
+    const uint32_t kh = lane128 >> 6;
+    const uint32_t ch = t >> 7;
+    const uint32_t slot = kh * 2 + ch;
+    const uint32_t rgrp = warp & 1;
+    const uint32_t lane_base = ((warp & 3) * 32u) << 16;
+    const uint32_t l_p_full0 = ptx::mapa(bar(bars.p_full[0]), 0);
+    const uint32_t l_p_full1 = ptx::mapa(bar(bars.p_full[1]), 0);
+    const float NEG_INF = -INFINITY;
+    uint32_t g = 0;
+    for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
+      const int mt = item % p.n_mtiles;
+      const int bh = item / p.n_mtiles;
+      const int h = bh % p.heads_q, b = bh / p.heads_q;
+      const int hk = h / group;
+      const int q0 = mt * 128;
+      const int T = num_kv_tiles(p, q0);
+      const int gq = q0 + 64 * (int)rank + (int)row;
+      const int causal_lim = gq + (p.seqlen_kv - p.seqlen_q);
+      const float qs_c = p.qs[((int64_t)b * p.heads_q + h) * p.tq + mt] * p.scale_log2;
+      const float* ksp = p.ks + ((int64_t)b * p.heads_kv + hk) * p.tk;
+      const float* vsp = p.vs + ((int64_t)b * p.heads_kv + hk) * p.tk;
+      const float vref = p.vref[(int64_t)b * p.heads_kv + hk];
+      const float pc_base = vref > 0.f ? kPScale / vref : 0.f;
+      float m = NEG_INF, l = 0.f;
+
+      for (int i = 0; i < T; ++i, ++g) {
+        const uint32_t sbuf = g & 1;
+        const float mul = qs_c * __ldg(ksp + i);      // dequant * softmax scale * log2(e)
+        const float pc = pc_base * __ldg(vsp + i);    // P -> e4m3 range, V scale folded in
+        ptx::mbar_wait(bar(bars.s_full[sbuf]), (g >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t sr[32];
+        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32 * ch, sr);
+        ptx::tmem_wait_ld();
+        float x[32];
+        const int key0 = i * 128 + 64 * (int)kh + 32 * (int)ch;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]) * mul;
+        const bool tail = (i * 128 + 128 > p.seqlen_kv);
+        const bool diag = p.causal && (i * 128 + 127 > q0 + (p.seqlen_kv - p.seqlen_q));
+        if (tail || diag) {
+          const int lim = p.causal ? (causal_lim < p.seqlen_kv - 1 ? causal_lim : p.seqlen_kv - 1) : p.seqlen_kv - 1;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (key0 + j > lim) x[j] = NEG_INF;
+        }
+        float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
+        float mx2 = fmax3(x[6], x[7], x[8]), mx3 = fmax3(x[9], x[10], x[11]);
+        mx0 = fmax3(mx0, x[12], x[13]); mx1 = fmax3(mx1, x[14], x[15]);
+        mx2 = fmax3(mx2, x[16], x[17]); mx3 = fmax3(mx3, x[18], x[19]);
+        mx0 = fmax3(mx0, x[20], x[21]); mx1 = fmax3(mx1, x[22], x[23]);
+        mx2 = fmax3(mx2, x[24], x[25]); mx3 = fmax3(mx3, x[26], x[27]);
+        mx0 = fmax3(mx0, x[28], x[29]); mx1 = fmax3(mx1, x[30], x[31]);
+        float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3);
+        xch[sbuf][slot][row] = tmax;
+        ptx::named_bar_sync(1 + rgrp, 128);
+        tmax = fmaxf(fmax3(xch[sbuf][0][row], xch[sbuf][1][row], xch[sbuf][2][row]), xch[sbuf][3][row]);
+        const float m_new = fmaxf(m, tmax);
+        const bool upd = (m_new - m) > kLazyThreshold;
+        const float m_use = upd ? m_new : m;
+        const bool need_rescale = upd && (m != NEG_INF);
+        const float m_safe = (m_use == NEG_INF) ? 0.f : m_use;
+        float factor = 1.f;
+        if (need_rescale) factor = exp2f(m - m_use);
+        uint32_t pk[8];
+        float lsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float e0 = exp2f(x[j] - m_safe), e1 = exp2f(x[j + 1] - m_safe);
+          const float e2 = exp2f(x[j + 2] - m_safe), e3 = exp2f(x[j + 3] - m_safe);
+          lsum += (e0 + e1) + (e2 + e3);
+          pk[j >> 2] = pack_e4m3x4(e0 * pc, e1 * pc, e2 * pc, e3 * pc);
+        }
+        l = l * factor + lsum;
+        m = m_use;
+
+        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((g >> 1) & 1) ^ 1);
+        {
+          // P8 tile: one 128-byte row per query row (128 keys), this thread owns bytes [64kh+32ch, +32)
+          const uint32_t prow = sP + sbuf * 8192 + row * 128;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t addr = prow + (((4 * kh + 2 * ch + c) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
+                         "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                         : "memory");
+          }
+        }
+        if (__any_sync(0xffffffffu, need_rescale)) {
+          ptx::mbar_wait(bar(bars.p_empty[(g - 1) & 1]), ((g - 1) >> 1) & 1);
+          ptx::tc_fence_after();
+#pragma unroll 1
+          for (int c0 = (int)ch * (Cfg::O_COLS / 2); c0 < (int)(ch + 1) * (Cfg::O_COLS / 2); c0 += 32) {
+            uint32_t orr[32];
+            ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * factor);
+            ptx::tmem_st_x32(tmem + lane_base + c0, orr);
+          }
+          ptx::tmem_wait_st();
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(sbuf ? l_p_full1 : l_p_full0);
+      }
+
+      // ---------------- epilogue ----------------
+      {
+        const uint32_t gl = g - 1;
+        ptx::mbar_wait(bar(bars.p_empty[gl & 1]), (gl >> 1) & 1);
+        ptx::tc_fence_after();
+        float (*xl)[64] = xch[gl & 1];
+        xl[slot][row] = l;
+        ptx::named_bar_sync(1 + rgrp, 128);
+        const float l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
+        const float inv = l_tot > 0.f ? (vref / kPScale) / l_tot : 0.f;
+        const bool row_ok = gq < p.seqlen_q;
+        uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
+                        2 * ((int64_t)b * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)gq * p.o_stride[2]);
+#pragma unroll
+        for (int s = 0; s < Cfg::NSLICE; ++s) {
+#pragma unroll 1
+          for (int c0 = (int)ch * 64; c0 < (int)(ch + 1) * 64; c0 += 32) {
+            uint32_t orr[32];
+            ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
+            ptx::tmem_wait_ld();
+            const int d0 = 256 * s + 128 * (int)kh + c0;
+            if (row_ok) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                const int d = d0 + 8 * v;
+                if (d < p.head_dim) {
+                  uint32_t w[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float a = __uint_as_float(orr[8 * v + 2 * u]) * inv;
+                    const float c = __uint_as_float(orr[8 * v + 2 * u + 1]) * inv;
+                    w[u] = OUT_BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
+                  }
+                  *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+              }
+            }
+          }
+        }
+        if (p.lse != nullptr && slot == 0 && row_ok) {
+          const float lse = (l_tot > 0.f) ? (m + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
+          p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
+        }
+        ptx::tc_fence_before();
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == kMmaWarp) ptx::tmem_dealloc<CG>(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused pre-pass: per-(b, h, 128-row block) amax -> scale = amax / 448, e4m3 rows padded to dpad
+// (multiple of 16 bytes), scales, and the per-(b, h) maximum V scale.
+// One 256-thread block per (tensor, b, h, block). (reference: quantize_fp8.cuh:67-168)
+// ------------------------------------------------------------------------------------------------
+struct QuantArgs {
+  const void* src[3];      // Q, K, V (16-bit)
+  uint8_t* dst[3];         // Q8, K8, V8  [B, H, N, dpad]
+  float* scale[3];         // [B, H, T]
+  float* vref;             // [B, Hkv]
+  int64_t stride[3][3];    // element strides (b, h, n) of the sources
+  int heads[3], seqlen[3], tiles[3];
+  int64_t first_block[4];  // prefix sums of blocks per tensor
+  int batch, head_dim, dpad;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) quantize_e4m3_kernel(const QuantArgs a) {
+  __shared__ float red[8];
+  const int64_t blk = blockIdx.x;
+  const int which = blk >= a.first_block[2] ? 2 : (blk >= a.first_block[1] ? 1 : 0);
+  const int64_t local = blk - a.first_block[which];
+  const int T = a.tiles[which], H = a.heads[which], N = a.seqlen[which];
+  const int tile = (int)(local % T);
+  const int h = (int)((local / T) % H);
+  const int b = (int)(local / ((int64_t)T * H));
+  const int D = a.head_dim, dpad = a.dpad;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(a.src[which]) +
+                       2 * ((int64_t)b * a.stride[which][0] + (int64_t)h * a.stride[which][1]);
+  const int64_t rs = a.stride[which][2];
+  const int r0 = tile * 128;
+  const int rows = (N - r0) < 128 ? (N - r0) : 128;
+  const int vec_per_row = D / 8;               // 8 elements (16 B) per vector; D % 8 == 0
+  const int nvec = rows * vec_per_row;
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    const int r = i / vec_per_row, c = i % vec_per_row;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + 2 * ((int64_t)(r0 + r) * rs + 8 * c));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f0, f1;
+      if (BF16) { f0 = __uint_as_float(w[u] << 16); f1 = __uint_as_float(w[u] & 0xffff0000u); }
+      else { const __half2 hh = *reinterpret_cast<const __half2*>(&w[u]); f0 = __low2float(hh); f1 = __high2float(hh); }
+      amax = fmaxf(amax, fmaxf(fabsf(f0), fabsf(f1)));
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i]);
+  const float scale = fmaxf(amax, 1e-12f) / 448.f;
+  const float inv = 1.f / scale;
+  if (threadIdx.x == 0) {
+    a.scale[which][((int64_t)b * H + h) * T + tile] = scale;
+    if (which == 2) atomicMax(reinterpret_cast<unsigned int*>(a.vref + (int64_t)b * H + h), __float_as_uint(scale));
+  }
+  uint8_t* dst = a.dst[which] + (((int64_t)b * H + h) * N + r0) * dpad;
+  const int ovec_per_row = dpad / 8;  // 8 output bytes per step
+  for (int i = threadIdx.x; i < rows * ovec_per_row; i += 256) {
+    const int r = i / ovec_per_row, c = i % ovec_per_row;
+    uint2 o = make_uint2(0u, 0u);
+    if (8 * c < D) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + 2 * ((int64_t)(r0 + r) * rs + 8 * c));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      float f[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (BF16) { f[2 * u] = __uint_as_float(w[u] << 16); f[2 * u + 1] = __uint_as_float(w[u] & 0xffff0000u); }
+        else { const __half2 hh = *reinterpret_cast<const __half2*>(&w[u]); f[2 * u] = __low2float(hh); f[2 * u + 1] = __high2float(hh); }
+      }
+      o.x = pack_e4m3x4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
+      o.y = pack_e4m3x4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
+    }
+    *reinterpret_cast<uint2*>(dst + (int64_t)r * dpad + 8 * c) = o;
+  }
+}
+
+template <int NB, bool OUT_BF16>
+static int launch_fp8_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                              const Fp8KernelParams& kp, int nclusters, cudaStream_t stream) {
+  using Cfg = Fp8Cfg<NB>;
+  auto kern = ffpa_fwd_fp8_kernel<NB, OUT_BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN);
+    if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(fp8 smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "fp8 forward launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return FFPA_OK;
+}
+
+}  // namespace fp8
+}  // namespace ffpa

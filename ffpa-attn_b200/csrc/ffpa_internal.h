@@ -43,6 +43,8 @@ int sm_count();
 
 int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream);
 int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream);
+int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream);
+uint64_t fwd_fp8_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim);
 uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv,
                              int head_dim);
 

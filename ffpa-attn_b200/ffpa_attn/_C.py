@@ -49,6 +49,7 @@ class _FwdParams(ctypes.Structure):
     ("fp8", ctypes.c_int32),
     ("softmax_scale", ctypes.c_float), ("dropout_p", ctypes.c_float),
     ("philox_seed", ctypes.c_uint64), ("philox_offset", ctypes.c_uint64),
+    ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64),
   ]
 
 
@@ -73,6 +74,8 @@ _lib.ffpa_b200_fwd.argtypes = [ctypes.POINTER(_FwdParams), ctypes.c_void_p]
 _lib.ffpa_b200_fwd.restype = ctypes.c_int
 _lib.ffpa_b200_bwd.argtypes = [ctypes.POINTER(_BwdParams), ctypes.c_void_p]
 _lib.ffpa_b200_bwd.restype = ctypes.c_int
+_lib.ffpa_b200_fwd_workspace_bytes.argtypes = [ctypes.c_int32] * 7
+_lib.ffpa_b200_fwd_workspace_bytes.restype = ctypes.c_uint64
 _lib.ffpa_b200_bwd_workspace_bytes.argtypes = [ctypes.c_int32] * 6
 _lib.ffpa_b200_bwd_workspace_bytes.restype = ctypes.c_uint64
 _lib.ffpa_b200_set_backend_impl.argtypes = [ctypes.c_int32]
@@ -211,6 +214,15 @@ def ffpa_attn_forward(Q, K, V, attn_bias, O, softmax_lse, stages, acc, causal, s
   p.dropout_p = float(dropout_p)
   p.philox_seed = int(philox_seed) & 0xFFFFFFFFFFFFFFFF
   p.philox_offset = int(philox_offset) & 0xFFFFFFFFFFFFFFFF
+  ws = None
+  if p.fp8:
+    # FP8 path (backend hint CUTE_TMA_FP8): scratch for the e4m3 copies of Q/K/V and their scales.
+    # The fp8_* knobs of the reference signature select sm_120 variants (per-thread scales, int8 QK,
+    # smooth-K/V, hybrid early rows); the sm_100a kernel implements per-block e4m3 only.
+    nbytes = int(_lib.ffpa_b200_fwd_workspace_bytes(p.batch, p.heads_q, p.heads_kv, p.seqlen_q,
+                                                     p.seqlen_kv, p.head_dim, 1))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=Q.device)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
   with torch.cuda.device(Q.device):
     stream = torch.cuda.current_stream(Q.device).cuda_stream
     rc = _lib.ffpa_b200_fwd(ctypes.byref(p), ctypes.c_void_p(stream))

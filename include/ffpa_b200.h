@@ -75,6 +75,10 @@ typedef struct ffpa_fwd_params {
   float dropout_p;
   uint64_t philox_seed;
   uint64_t philox_offset;
+  /* scratch for the FP8 path (quantised copies + scales): ffpa_b200_fwd_workspace_bytes() bytes,
+   * 256-byte aligned device memory; ignored (may be NULL) when fp8 == 0 */
+  void* workspace;
+  uint64_t workspace_bytes;
 } ffpa_fwd_params;
 
 typedef struct ffpa_bwd_params {
@@ -100,6 +104,11 @@ typedef struct ffpa_bwd_params {
 
 /* replaces ffpa_attn_forward (/root/reference/csrc/cuffpa/ffpa_api.cc:86-239) */
 int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream);
+
+/* scratch bytes ffpa_b200_fwd needs for these sizes (0 unless fp8 != 0) */
+uint64_t ffpa_b200_fwd_workspace_bytes(int32_t batch, int32_t heads_q, int32_t heads_kv,
+                                       int32_t seqlen_q, int32_t seqlen_kv, int32_t head_dim,
+                                       int32_t fp8);
 
 /* replaces ffpa_attn_backward (/root/reference/csrc/cuffpa/ffpa_api.cc:242-263, a thrower there) */
 int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream);

