@@ -130,6 +130,10 @@ def cpu_sdpa_sample(Hq, Hkv, Nq, Nkv, D, causal, budget_s, max_heads=None):
   Returns (tflops, heads_used, seconds, threads)."""
   from oracle import attention_oracle as orc
 
+  # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use the host's cores
+  want = max(1, (os.cpu_count() or 2) // 2)
+  if torch.get_num_threads() < want:
+    torch.set_num_threads(want)
   threads = torch.get_num_threads()
   group = Hq // Hkv
   torch.manual_seed(42)
@@ -387,7 +391,7 @@ def main():
 
   # ---- CPU baseline on this box's host cores (bounded sample) ----
   cpu = None
-  if not args.no_cpu_baseline:
+  if not args.no_cpu_baseline and world == 1:
     tf, heads, secs, threads = cpu_sdpa_sample(Hq, Hkv, Nq, Nkv, D, causal, budget_s=12.0)
     cpu = {"value": tf, "unit": "TFLOP/s", "cores": threads, "kind": "port",
            "sample": f"{heads} of {Hq} heads of the same workload, one pass, {secs:.2f} s, aten SDPA bf16 on host "

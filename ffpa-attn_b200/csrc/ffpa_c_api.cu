@@ -1,7 +1,10 @@
 // C ABI (include/ffpa_b200.h): argument validation mirroring the reference launcher's TORCH_CHECK
 // contract (/root/reference/csrc/cuffpa/launch.cuh:79-129, ffpa_api.cc:53-62,180-205), then dispatch
 // to the sm_100a kernels. No torch types, no host synchronisation, no CPU fallback.
+#include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -33,6 +36,64 @@ int sm_count() {
     cached[dev] = n > 0 ? n : 148;
   }
   return cached[dev];
+}
+
+// ---------------------------------------------------------------------------------------------
+// balanced schedules: greedy list scheduling (longest processing time first within each group of
+// n_items/groups consecutive items keeps the head-major order, hence the L2 reuse of K/V).
+// ---------------------------------------------------------------------------------------------
+struct SchedEntry { std::vector<int> cost; int nclusters; int stride; int* dev; int device; };
+static std::mutex g_sched_mu;
+static std::vector<SchedEntry> g_sched;
+
+const int* get_schedule(const int* cost, int n_items, int nclusters, int* stride_out, cudaStream_t stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_sched_mu);
+  if (g_sched.size() >= 256) return nullptr;  // tables are never freed (kernels may still read them): cap the cache
+  for (auto& e : g_sched)
+    if (e.device == dev && e.nclusters == nclusters && (int)e.cost.size() == n_items &&
+        std::memcmp(e.cost.data(), cost, sizeof(int) * n_items) == 0) {
+      *stride_out = e.stride;
+      return e.dev;
+    }
+  // order: keep the caller's grouping (items arrive head-major, m-tile fastest); inside each run of
+  // increasing cost take the longest first
+  std::vector<int> order(n_items);
+  for (int i = 0; i < n_items; ++i) order[i] = i;
+  int run = 0;
+  while (run < n_items) {
+    int end = run + 1;
+    while (end < n_items && cost[end] >= cost[end - 1]) ++end;
+    std::reverse(order.begin() + run, order.begin() + end);
+    run = end;
+  }
+  std::vector<long long> load(nclusters, 0);
+  std::vector<std::vector<int>> lists(nclusters);
+  for (int idx : order) {
+    int best = 0;
+    for (int c = 1; c < nclusters; ++c)
+      if (load[c] < load[best]) best = c;
+    load[best] += cost[idx];
+    lists[best].push_back(idx);
+  }
+  size_t stride = 0;
+  for (auto& l : lists) stride = l.size() > stride ? l.size() : stride;
+  stride += 1;  // room for the -1 terminator
+  std::vector<int> table((size_t)nclusters * stride, -1);
+  for (int c = 0; c < nclusters; ++c)
+    for (size_t k = 0; k < lists[c].size(); ++k) table[(size_t)c * stride + k] = lists[c][k];
+  int* d = nullptr;
+  if (cudaMalloc(&d, table.size() * sizeof(int)) != cudaSuccess) return nullptr;
+  // synchronous copy: happens once per shape; the table is immutable afterwards
+  if (cudaMemcpy(d, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d);
+    return nullptr;
+  }
+  (void)stream;
+  g_sched.push_back(SchedEntry{std::vector<int>(cost, cost + n_items), nclusters, (int)stride, d, dev});
+  *stride_out = (int)stride;
+  return d;
 }
 
 static int check_device() {

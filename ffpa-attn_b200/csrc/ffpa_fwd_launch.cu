@@ -1,6 +1,7 @@
 // Host launcher of the forward: tensor-map construction (passed as __grid_constant__ kernel
 // parameters -- no per-launch cudaMalloc/cudaMemcpy as in
 // /root/reference/csrc/cuffpa/native/launch.cuh:503-509), persistent grid sizing, mode selection.
+#include <vector>
 #include "ffpa_internal.h"
 #include "sm100_ptx.cuh"
 
@@ -54,6 +55,21 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
 
   int nclusters = sm_count() / 2;
   if (nclusters > kp.n_items) nclusters = kp.n_items;
+  kp.sched = nullptr;
+  kp.sched_stride = 0;
+  if (a.causal && kp.n_items > nclusters) {
+    // causal items differ in length: balance them over the persistent clusters (greedy LPT over a
+    // head-major, longest-first order; table cached on the device per shape)
+    std::vector<int> cost((size_t)kp.n_items);
+    const int off = a.seqlen_kv - a.seqlen_q, tc = (a.seqlen_kv + 127) / 128;
+    for (int it = 0; it < kp.n_items; ++it) {
+      const int mt = it % kp.n_mtiles;
+      int t = ((mt * 128 + 127 + off) >> 7) + 1;
+      t = t < tc ? t : tc;
+      cost[it] = (t < 1 ? 1 : t) * 16 + 24;  // tiles + fixed per-item overhead (prologue/epilogue ~1.5 tiles)
+    }
+    kp.sched = get_schedule(cost.data(), kp.n_items, nclusters, &kp.sched_stride, stream);
+  }
   int mode = 0;  // fast
   if (a.dropout_p > 0.f) mode = 2;
   else if (a.bias_kind != FFPA_BIAS_NONE || !(a.softmax_scale > 0.f)) mode = 1;

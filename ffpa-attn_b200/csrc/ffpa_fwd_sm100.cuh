@@ -79,6 +79,14 @@ __device__ __forceinline__ int num_kv_tiles(const FwdKernelParams& p, int q0) {
   return tc < 1 ? 1 : tc;
 }
 
+// k-th work item of this cluster: from the balanced schedule table when present (causal), else
+// static round robin. Every role of both CTAs evaluates the same sequence.
+__device__ __forceinline__ int next_item(const FwdKernelParams& p, uint32_t cluster, uint32_t nclusters, uint32_t k) {
+  if (p.sched != nullptr) return (k < (uint32_t)p.sched_stride) ? __ldg(p.sched + (size_t)cluster * p.sched_stride + k) : -1;
+  const uint32_t item = cluster + k * nclusters;
+  return item < (uint32_t)p.n_items ? (int)item : -1;
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr) {
   // Philox-4x32-10, counter = (ctr_lo, ctr_hi, 0, 0), key = seed. Same generator as
   // /root/reference/csrc/cuffpa/native/prefill.cuh:398-422 (and curand / torch SDPA).
@@ -176,7 +184,10 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (ptx::elect_one()) {
       uint32_t kc = 0, vc = 0, it = 0;
       const uint32_t l_q_full = ptx::mapa(bar(bars.q_full), 0);
-      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters, ++it) {
+      for (uint32_t kidx = 0;; ++kidx, ++it) {
+        const int item_s = next_item(p, cluster, nclusters, kidx);
+        if (item_s < 0) break;
+        const uint32_t item = (uint32_t)item_s;
         const int mt = item % p.n_mtiles;
         const int pass = (item / p.n_mtiles) % Cfg::NPASS;
         const int bh = item / (p.n_mtiles * Cfg::NPASS);
@@ -233,7 +244,10 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       constexpr uint32_t fmt = BF16 ? 1u : 0u;
       constexpr uint32_t idesc_qk = ptx::make_idesc(fmt, fmt, 0, 0, 128, 128);
       uint32_t kc = 0, vc = 0, it = 0, g = 0, gp = 0;
-      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters, ++it) {
+      for (uint32_t kidx = 0;; ++kidx, ++it) {
+        const int item_s = next_item(p, cluster, nclusters, kidx);
+        if (item_s < 0) break;
+        const uint32_t item = (uint32_t)item_s;
         const int mt = item % p.n_mtiles;
         const int pass = (item / p.n_mtiles) % Cfg::NPASS;
         const int dvw = Cfg::slab_w(pass);
@@ -310,7 +324,10 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // softmax domain: fast mode works on raw scores (mul = scale*log2e), general on scaled+biased
     const float mul = (MODE == kModeFast) ? p.scale_log2 : 1.0f;
     uint32_t g = 0;
-    for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
+    for (uint32_t kidx = 0;; ++kidx) {
+      const int item_s = next_item(p, cluster, nclusters, kidx);
+      if (item_s < 0) break;
+      const uint32_t item = (uint32_t)item_s;
       const int mt = item % p.n_mtiles;
       const int pass = (item / p.n_mtiles) % Cfg::NPASS;
       const int bh = item / (p.n_mtiles * Cfg::NPASS);

@@ -19,6 +19,10 @@ struct FwdKernelParams {
   float dropout_p;
   uint64_t philox_seed, philox_offset;
   int n_mtiles, n_items;
+  // optional work schedule (causal load balancing): sched[cluster * sched_stride + k] = item id,
+  // -1 terminates; nullptr -> static round robin item = cluster + k * nclusters
+  const int* sched;
+  int sched_stride;
 };
 
 namespace bwd {
@@ -36,6 +40,9 @@ struct BwdKernelParams {
   int n_rtiles, n_items;   // row tiles (128 stationary rows) per (b, head); total items
 };
 }  // namespace bwd
+
+// balanced (greedy LPT) item schedule, cached per shape on the device; returns nullptr on failure
+const int* get_schedule(const int* cost, int n_items, int nclusters, int* stride_out, cudaStream_t stream);
 
 int set_error(int code, const char* fmt, ...);
 void count_launch();
