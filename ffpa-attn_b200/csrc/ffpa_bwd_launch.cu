@@ -63,6 +63,11 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   kp.lse2 = lse2; kp.delta = delta; kp.nq_pad = nq_pad;
   kp.batch = B; kp.heads_q = Hq; kp.heads_kv = Hkv; kp.seqlen_q = Nq; kp.seqlen_kv = Nkv; kp.head_dim = D;
   kp.causal = a.causal; kp.scale = a.softmax_scale; kp.scale_log2 = a.softmax_scale * 1.4426950408889634f;
+  kp.bias = a.bias_kind != FFPA_BIAS_NONE ? a.bias : nullptr;
+  kp.bias_kind = a.bias_kind;
+  for (int i = 0; i < 4; ++i) kp.bias_stride[i] = a.bias_stride[i];
+  kp.dropout_p = a.dropout_p; kp.philox_seed = a.philox_seed; kp.philox_offset = a.philox_offset;
+  kp.dbias = a.d_bias;
   const int max_clusters = sm_count() / 2;
   auto run = [&](int kind, void* out, const int64_t* ostride, int rows, int heads, const CUtensorMap& a1,
                  const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2, const CUtensorMap& b3) {

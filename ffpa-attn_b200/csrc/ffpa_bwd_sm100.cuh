@@ -63,6 +63,22 @@ struct Barriers {
   uint64_t t_full[2], t_empty[2];
 };
 
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0, c3 = 0;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t o0 = c0, o2 = c2;
+    c0 = __umulhi(0xCD9E8D57u, o2) ^ c1 ^ k0;
+    c2 = __umulhi(0xD2511F53u, o0) ^ c3 ^ k1;
+    c1 = 0xCD9E8D57u * o2;
+    c3 = 0xD2511F53u * o0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
 // streamed-tile range of an item
 struct TileRange { int first, count; };
 
@@ -87,7 +103,7 @@ __device__ __forceinline__ TileRange col_tiles(const BwdKernelParams& p, int r0)
   }
 }
 
-template <int NQK, bool BF16, int KIND>
+template <int NQK, bool BF16, int KIND, bool GENERAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
@@ -344,6 +360,10 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           if (p.causal) lim_lo = grow - off;
         }
         uint32_t pk[16];
+        // GENERAL: additive bias, Philox dropout replay, dBias output (dQ kind). Query / key of
+        // element jj: dQ kind (q = grow, key = col), dK/dV kinds (q = col, key = grow).
+        const int hq_cur = (KIND == kKindDQ) ? hs : hs * group + gi;
+        const float inv_keep = GENERAL ? 1.f / (1.f - p.dropout_p) : 1.f;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float e[2];
@@ -358,10 +378,44 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
               if (HAS_DP) { const float4 d4 = c_dl[jj >> 2]; dl = (jj & 3) == 0 ? d4.x : (jj & 3) == 1 ? d4.y : (jj & 3) == 2 ? d4.z : d4.w; }
               else dl = 0.f;
             }
-            float pe = exp2f(fmaf(__uint_as_float(sr[jj]), p.scale_log2, -l2));
             const int col = col0 + jj;
+            const int qi = (KIND == kKindDQ) ? grow : col;
+            const int ki = (KIND == kKindDQ) ? col : grow;
+            float xs = fmaf(__uint_as_float(sr[jj]), p.scale_log2, -l2);
+            float mult = 1.f;
+            if constexpr (GENERAL) {
+              const bool inb = qi < p.seqlen_q && ki < p.seqlen_kv;
+              if (p.bias_kind != 0 && inb) {
+                const int64_t bo = (int64_t)b * p.bias_stride[0] + (int64_t)hq_cur * p.bias_stride[1] +
+                                   (int64_t)qi * p.bias_stride[2] + ki;
+                float bv;
+                if (p.bias_kind == 1) bv = reinterpret_cast<const float*>(p.bias)[bo];
+                else if (BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[bo]);
+                else bv = __half2float(reinterpret_cast<const __half*>(p.bias)[bo]);
+                xs = fmaf(bv, 1.4426950408889634f, xs);
+              }
+              if (p.dropout_p > 0.f && inb) {
+                const uint64_t eo = p.philox_offset +
+                    ((uint64_t)((int64_t)b * p.heads_q + hq_cur) * (uint64_t)p.seqlen_q + (uint64_t)qi) * (uint64_t)p.seqlen_kv + (uint64_t)ki;
+                const uint4 r4 = philox4x32_10(p.philox_seed, eo >> 2);
+                const uint32_t sel = (uint32_t)(eo & 3);
+                const uint32_t rv = sel == 0 ? r4.x : sel == 1 ? r4.y : sel == 2 ? r4.z : r4.w;
+                const float uni = ((float)rv + 1.0f) * 2.3283064365386963e-10f;
+                mult = (uni > p.dropout_p) ? inv_keep : 0.f;
+              }
+            }
+            float pe = exp2f(xs);
             if (col < lim_lo || col > lim_hi) pe = 0.f;
-            e[u] = HAS_DP ? pe * (__uint_as_float(dr[jj]) - dl) : pe;
+            if (HAS_DP) {
+              const float ds = pe * (__uint_as_float(dr[jj]) * mult - dl);
+              e[u] = ds;
+              if constexpr (GENERAL && KIND == kKindDQ) {
+                if (p.dbias != nullptr && qi < p.seqlen_q && ki < p.seqlen_kv)
+                  p.dbias[(((int64_t)b * p.heads_q + hq_cur) * p.seqlen_q + qi) * (int64_t)p.seqlen_kv + ki] = ds;
+              }
+            } else {
+              e[u] = pe * mult;
+            }
           }
           pk[j >> 1] = BF16 ? ptx::pack_bf16x2(e[0], e[1]) : ptx::pack_f16x2(e[0], e[1]);
         }
@@ -474,12 +528,12 @@ __global__ void bwd_preprocess_kernel(const void* __restrict__ o, const void* __
 }
 
 
-template <int NQK, bool BF16, int KIND>
+template <int NQK, bool BF16, int KIND, bool GENERAL>
 static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
                               const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp,
                               int nclusters, cudaStream_t stream) {
   using Cfg = BwdCfg<NQK, KIND>;
-  auto kern = ffpa_bwd_kernel<NQK, BF16, KIND>;
+  auto kern = ffpa_bwd_kernel<NQK, BF16, KIND, GENERAL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN);
@@ -493,19 +547,19 @@ static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, cons
   return FFPA_OK;
 }
 
-template <bool BF16, int KIND>
+template <bool BF16, int KIND, bool GENERAL>
 static int dispatch_bwd_nqk(int nqk, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
                             const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp,
                             int nclusters, cudaStream_t stream) {
   switch (nqk) {
-    case 1: return launch_bwd_variant<1, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 2: return launch_bwd_variant<2, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 3: return launch_bwd_variant<3, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 4: return launch_bwd_variant<4, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 5: return launch_bwd_variant<5, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 6: return launch_bwd_variant<6, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 7: return launch_bwd_variant<7, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 8: return launch_bwd_variant<8, BF16, KIND>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 1: return launch_bwd_variant<1, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 2: return launch_bwd_variant<2, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 3: return launch_bwd_variant<3, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 4: return launch_bwd_variant<4, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 5: return launch_bwd_variant<5, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 6: return launch_bwd_variant<6, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 7: return launch_bwd_variant<7, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 8: return launch_bwd_variant<8, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
     default: return set_error(FFPA_ERR_UNSUPPORTED, "backward supports head_dim <= 512");
   }
 }
@@ -515,9 +569,15 @@ template <bool BF16>
 int dispatch_bwd_dtype(int nqk, int kind, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
                        const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp, int nclusters,
                        cudaStream_t stream) {
-  if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
-  if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
-  return dispatch_bwd_nqk<BF16, kKindDV>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+  const bool general = kp.bias_kind != 0 || kp.dropout_p > 0.f || kp.dbias != nullptr;
+  if (general) {
+    if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, true>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+    if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, true>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+    return dispatch_bwd_nqk<BF16, kKindDV, true>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+  }
+  if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, false>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+  if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, false>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+  return dispatch_bwd_nqk<BF16, kKindDV, false>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
 }
 
 template <bool BF16>

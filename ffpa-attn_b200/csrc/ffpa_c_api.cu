@@ -189,6 +189,15 @@ int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream) {
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "causal attention requires Nkv >= Nq");
   if (p->head_dim > 512)
     return set_error(FFPA_ERR_UNSUPPORTED, "backward kernels support head_dim <= 512 (got %d)", p->head_dim);
+  if (p->bias_kind != FFPA_BIAS_NONE) {
+    if (p->causal) return set_error(FFPA_ERR_INVALID_ARGUMENT, "attn bias and causal masking are mutually exclusive");
+    if (p->bias_kind != FFPA_BIAS_F32 && p->bias_kind != FFPA_BIAS_QDTYPE)
+      return set_error(FFPA_ERR_INVALID_ARGUMENT, "attn bias dtype must be fp32 or match Q");
+    if (!p->bias || p->bias_stride[3] != 1)
+      return set_error(FFPA_ERR_INVALID_ARGUMENT, "attn bias must be non-NULL with a contiguous last dim");
+  }
+  if (!(p->dropout_p >= 0.f && p->dropout_p < 1.f))
+    return set_error(FFPA_ERR_INVALID_ARGUMENT, "dropout_p must be in [0, 1), got %f", (double)p->dropout_p);
   const int32_t qd[3] = {p->batch, p->heads_q, p->seqlen_q};
   const int32_t kd[3] = {p->batch, p->heads_kv, p->seqlen_kv};
   if (int e = check_strides("Q", p->q_stride, qd)) return e;

@@ -38,6 +38,13 @@ struct BwdKernelParams {
   float scale_log2;        // softmax_scale * log2(e)
   float scale;             // softmax_scale
   int n_rtiles, n_items;   // row tiles (128 stationary rows) per (b, head); total items
+  // GENERAL variants: additive bias, dropout replay, dBias (fp32 [B, Hq, Nq, Nkv], dQ kind writes it)
+  const void* bias;
+  int64_t bias_stride[4];
+  int bias_kind;
+  float dropout_p;
+  uint64_t philox_seed, philox_offset;
+  float* dbias;
 };
 }  // namespace bwd
 

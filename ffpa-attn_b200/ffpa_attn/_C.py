@@ -67,6 +67,9 @@ class _BwdParams(ctypes.Structure):
     ("dtype", ctypes.c_int32), ("causal", ctypes.c_int32),
     ("softmax_scale", ctypes.c_float),
     ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64),
+    ("bias", ctypes.c_void_p), ("bias_stride", ctypes.c_int64 * 4), ("bias_kind", ctypes.c_int32),
+    ("dropout_p", ctypes.c_float), ("philox_seed", ctypes.c_uint64), ("philox_offset", ctypes.c_uint64),
+    ("d_bias", ctypes.c_void_p),
   ]
 
 
@@ -131,6 +134,32 @@ def _strides4(t: torch.Tensor):
   return (ctypes.c_int64 * 4)(*[int(s) for s in t.stride()])
 
 
+def _bias_fields(attn_bias, Q, K):
+  """(tensor kept alive, bias_kind, strides[4], data_ptr) following native/launch.cuh:277-290:
+  4-D [1|B, 1|Hq, 1|Nq, 1|Nkv], fp32 or Q's dtype, last dim contiguous, broadcast dims stride 0."""
+  if attn_bias is None or attn_bias.numel() == 0:
+    return None, 0, (ctypes.c_int64 * 4)(0, 0, 0, 0), None
+  _check_cuda(Q, attn_bias)
+  if attn_bias.dim() != 4:
+    raise RuntimeError("ffpa_attn: attn_bias must be 4-D [1|B, 1|Hq, 1|Nq, 1|Nkv]")
+  want = (Q.size(0), Q.size(1), Q.size(2), K.size(2))
+  for i in range(4):
+    if attn_bias.size(i) not in (1, want[i]):
+      raise RuntimeError(f"ffpa_attn: attn_bias dim {i} must be 1 or {want[i]}")
+  if attn_bias.dtype == torch.float32:
+    kind = 1
+  elif attn_bias.dtype == Q.dtype:
+    kind = 2
+  else:
+    raise RuntimeError("ffpa_attn: attn_bias dtype must be float32 or match Q")
+  if attn_bias.size(3) == 1 and K.size(2) != 1:
+    attn_bias = attn_bias.expand(-1, -1, -1, K.size(2)).contiguous()
+  elif attn_bias.stride(3) != 1:
+    raise RuntimeError("ffpa_attn: attn_bias last dim must be contiguous")
+  bs = [0 if attn_bias.size(i) == 1 else int(attn_bias.stride(i)) for i in range(3)] + [1]
+  return attn_bias, kind, (ctypes.c_int64 * 4)(*bs), attn_bias.data_ptr()
+
+
 def launch_count() -> int:
   """Kernels launched by the library since load (bench.py reports it as ``gpu_launches``)."""
   return int(_lib.ffpa_b200_launch_count())
@@ -179,32 +208,7 @@ def ffpa_attn_forward(Q, K, V, attn_bias, O, softmax_lse, stages, acc, causal, s
   else:
     p.lse = None
   p.q_stride, p.k_stride, p.v_stride, p.o_stride = _strides4(Q), _strides4(K), _strides4(V), _strides4(O)
-  has_bias = attn_bias is not None and attn_bias.numel() > 0
-  if has_bias:
-    _check_cuda(Q, attn_bias)
-    if attn_bias.dim() != 4:
-      raise RuntimeError("ffpa_attn_forward: attn_bias must be 4-D [1|B, 1|Hq, 1|Nq, 1|Nkv]")
-    want = (Q.size(0), Q.size(1), Q.size(2), K.size(2))
-    for i in range(4):
-      if attn_bias.size(i) not in (1, want[i]):
-        raise RuntimeError(f"ffpa_attn_forward: attn_bias dim {i} must be 1 or {want[i]}")
-    if attn_bias.dtype == torch.float32:
-      p.bias_kind = 1
-    elif attn_bias.dtype == Q.dtype:
-      p.bias_kind = 2
-    else:
-      raise RuntimeError("ffpa_attn_forward: attn_bias dtype must be float32 or match Q")
-    if attn_bias.size(3) == 1 and K.size(2) != 1:
-      attn_bias = attn_bias.expand(-1, -1, -1, K.size(2)).contiguous()
-    elif attn_bias.stride(3) != 1:
-      raise RuntimeError("ffpa_attn_forward: attn_bias last dim must be contiguous")
-    # broadcast dims get stride 0 (native/launch.cuh:277-290)
-    bs = [0 if attn_bias.size(i) == 1 else int(attn_bias.stride(i)) for i in range(3)] + [1]
-    p.bias_stride = (ctypes.c_int64 * 4)(*bs)
-    p.bias = attn_bias.data_ptr()
-  else:
-    p.bias_kind = 0
-    p.bias = None
+  _bias_keep, p.bias_kind, p.bias_stride, p.bias = _bias_fields(attn_bias, Q, K)
   p.batch, p.heads_q, p.seqlen_q, p.head_dim = Q.size(0), Q.size(1), Q.size(2), Q.size(3)
   p.heads_kv, p.seqlen_kv = K.size(1), K.size(2)
   p.dtype = dt
@@ -230,8 +234,11 @@ def ffpa_attn_forward(Q, K, V, attn_bias, O, softmax_lse, stages, acc, causal, s
     _raise(rc)
 
 
-def ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale) -> None:
-  """Signature of ffpa_api.cc:242-246 (a thrower in the reference); real here once built."""
+def ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale,
+                       attn_bias=None, dropout_p=0.0, philox_seed=0, philox_offset=0, d_bias=None) -> None:
+  """Positional signature of ffpa_api.cc:242-246 (a thrower in the reference); real here.
+  Keyword extras replay what the forward applied: additive ``attn_bias``, dropout (same Philox
+  seed/offset) and ``d_bias`` -- an fp32 [B, Hq, Nq, Nkv] buffer that receives dS per score."""
   _check_cuda(Q, K, V, O, dO, dQ, dK, dV, softmax_lse)
   dt = _dtype_code(Q)
   p = _BwdParams()
@@ -252,6 +259,17 @@ def ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, 
                                                    p.seqlen_kv, p.head_dim))
   ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=Q.device)
   p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+  _bias_keep, p.bias_kind, p.bias_stride, p.bias = _bias_fields(attn_bias, Q, K)
+  p.dropout_p = float(dropout_p)
+  p.philox_seed = int(philox_seed) & 0xFFFFFFFFFFFFFFFF
+  p.philox_offset = int(philox_offset) & 0xFFFFFFFFFFFFFFFF
+  if d_bias is not None:
+    if d_bias.dtype != torch.float32 or not d_bias.is_contiguous() or \
+        tuple(d_bias.shape) != (Q.size(0), Q.size(1), Q.size(2), K.size(2)):
+      raise RuntimeError("ffpa_attn_backward: d_bias must be contiguous fp32 [B, Hq, Nq, Nkv]")
+    p.d_bias = d_bias.data_ptr()
+  else:
+    p.d_bias = None
   with torch.cuda.device(Q.device):
     stream = torch.cuda.current_stream(Q.device).cuda_stream
     rc = _lib.ffpa_b200_bwd(ctypes.byref(p), ctypes.c_void_p(stream))

@@ -102,6 +102,47 @@ def _bwd_cuda_fake(Q, K, V, O, softmax_lse, dO, stages, causal, softmax_scale):
           torch.empty_like(V, memory_format=torch.contiguous_format))
 
 
+# extended backward: replays bias / dropout and optionally returns the bias gradient (reduced over the
+# bias' broadcast dims, cast to its dtype) -- the math of the reference's Triton backward
+# (/root/reference/src/ffpa_attn/triton/_ffpa_bwd.py:692-855) on the sm_100a kernels.
+torch.library.define(
+  f"{_OP_NAMESPACE}::_bwd_cuda_ex",
+  "(Tensor q, Tensor k, Tensor v, Tensor o, Tensor softmax_lse, Tensor d_o, Tensor attn_bias, int stages, "
+  "int causal, float softmax_scale, float dropout_p, int philox_seed, int philox_offset, bool bias_grad) -> "
+  "(Tensor dq, Tensor dk, Tensor dv, Tensor dbias)",
+)
+
+
+@torch.library.impl(f"{_OP_NAMESPACE}::_bwd_cuda_ex", "CUDA")
+def _bwd_cuda_ex_torch_op(Q, K, V, O, softmax_lse, dO, attn_bias, stages, causal, softmax_scale, dropout_p,
+                          philox_seed, philox_offset, bias_grad):
+  dQ = torch.empty_like(Q, memory_format=torch.contiguous_format)
+  dK = torch.empty_like(K, memory_format=torch.contiguous_format)
+  dV = torch.empty_like(V, memory_format=torch.contiguous_format)
+  has_bias = attn_bias.numel() > 0
+  d_full = None
+  if bias_grad and has_bias:
+    d_full = torch.zeros(Q.size(0), Q.size(1), Q.size(2), K.size(2), dtype=torch.float32, device=Q.device)
+  _cuda_ext.ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale,
+                               attn_bias=attn_bias if has_bias else None, dropout_p=dropout_p,
+                               philox_seed=philox_seed, philox_offset=philox_offset, d_bias=d_full)
+  if d_full is not None:
+    red = [i for i in range(4) if attn_bias.size(i) == 1 and d_full.size(i) != 1]
+    dbias = (d_full.sum(dim=red, keepdim=True) if red else d_full).to(attn_bias.dtype)
+  else:
+    dbias = Q.new_empty(0)
+  return dQ, dK, dV, dbias
+
+
+@torch.library.register_fake(f"{_OP_NAMESPACE}::_bwd_cuda_ex")
+def _bwd_cuda_ex_fake(Q, K, V, O, softmax_lse, dO, attn_bias, stages, causal, softmax_scale, dropout_p,
+                      philox_seed, philox_offset, bias_grad):
+  dbias = torch.empty_like(attn_bias) if (bias_grad and attn_bias.numel() > 0) else Q.new_empty(0)
+  return (torch.empty_like(Q, memory_format=torch.contiguous_format),
+          torch.empty_like(K, memory_format=torch.contiguous_format),
+          torch.empty_like(V, memory_format=torch.contiguous_format), dbias)
+
+
 def _ffpa_attn_forward_cuda(Q, K, V, O, attn_bias, stages, acc, causal, softmax_scale,
                             dropout_p=0.0, philox_seed=0, philox_offset=0, fp8_smooth_k=True,
                             fp8_smooth_v=False, fp8_q_quant_method=0, fp8_k_quant_method=0,

@@ -313,15 +313,25 @@ class _FFPAAttnFunc(torch.autograd.Function):
     meta: FFPAAttnMeta = ctx.meta
     if not CUDA_BWD_AVAILABLE:
       raise NotImplementedError("the sm_100a backward kernels are not built into libffpa_b200.so")
-    if ctx.attn_bias is not None or meta.attn_meta.dropout_p > 0.0:
-      raise NotImplementedError(
-        "ffpa_attn backward with attn_mask / dropout is not implemented by the sm_100a kernels yet")
     if q.size(-1) > 512:
       raise NotImplementedError("ffpa_attn backward supports head_dim <= 512 on sm_100a (TMEM capacity)")
-    dq, dk, dv = _ffpa_attn_backward_cuda(
-      q, k, v, O, lse, d_o.contiguous(), meta.backward_meta.stages, int(meta.attn_meta.is_causal),
-      meta.attn_meta.scale)
-    return dq, dk, dv, None, None
+    bias = ctx.attn_bias
+    p_drop = meta.attn_meta.dropout_p
+    stages = meta.backward_meta.stages
+    if bias is None and p_drop <= 0.0:
+      dq, dk, dv = _ffpa_attn_backward_cuda(
+        q, k, v, O, lse, d_o.contiguous(), stages, int(meta.attn_meta.is_causal), meta.attn_meta.scale)
+      return dq, dk, dv, None, None
+    # bias and/or dropout: replay them in the backward kernels; dBias = P * (dP - delta)
+    # (reference math: triton/_ffpa_bwd.py:692-855; returned tuple: functional.py:1081-1172)
+    want_dbias = bias is not None and bias.requires_grad
+    seed = int(rng_state[0].item()) if rng_state.numel() else 0
+    offset = int(rng_state[1].item()) if rng_state.numel() else 0
+    dq, dk, dv, dbias = torch.ops.ffpa_attn._bwd_cuda_ex(
+      q, k, v, O, lse, d_o.contiguous(), bias if bias is not None else q.new_empty(0),
+      int(stages) if stages is not None else 0, int(meta.attn_meta.is_causal), float(meta.attn_meta.scale),
+      float(p_drop), seed, offset, bool(want_dbias))
+    return dq, dk, dv, (dbias if want_dbias else None), None
 
 
 @torch._dynamo.disable

@@ -100,6 +100,17 @@ typedef struct ffpa_bwd_params {
   /* scratch: fp32 workspace of ffpa_b200_bwd_workspace_bytes() bytes (device) */
   void* workspace;
   uint64_t workspace_bytes;
+  /* optional pieces of the forward that must be replayed (all zero / NULL when unused):
+   * additive bias (same conventions as ffpa_fwd_params), dropout (same Philox seed/offset as the
+   * forward), and d_bias: fp32 [B, Hq, Nq, Nkv] contiguous, receives dS = P*(dP - delta) per
+   * score (the caller reduces over the bias' broadcast dims); NULL = not wanted. */
+  const void* bias;
+  int64_t bias_stride[4];
+  int32_t bias_kind;
+  float dropout_p;
+  uint64_t philox_seed;
+  uint64_t philox_offset;
+  float* d_bias;
 } ffpa_bwd_params;
 
 /* replaces ffpa_attn_forward (/root/reference/csrc/cuffpa/ffpa_api.cc:86-239) */

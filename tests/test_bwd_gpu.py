@@ -148,6 +148,69 @@ def test_c3_full_size_gqa_causal_backward():
       assert cos > 0.999, f"{name} kv-head {hk}: cosine {cos}"  # tests/test_ffpa_cute_sm100.py:822-842
 
 
+@pytest.mark.parametrize("kind", ["add_full_f32", "add_bcast_qdtype", "key_bias", "bool"])
+def test_backward_with_attn_mask_and_bias_grad(kind):
+  """mask-grad path (/root/reference/tests/test_ffpa_bwd.py mask-grad cases; math
+  triton/_ffpa_bwd.py:692-855): dQ/dK/dV with an additive bias, and dBias = P*(dP - delta)
+  reduced over the bias' broadcast dims."""
+  import ffpa_attn
+
+  B, H, Nq, Nkv, D = 2, 2, 130, 200, 128
+  q, k, v, d_o = _mk(B, H, H, Nq, Nkv, D, torch.bfloat16, seed=5)
+  g = torch.Generator().manual_seed(9)
+  if kind == "add_full_f32":
+    bias = torch.randn(B, H, Nq, Nkv, generator=g)
+  elif kind == "add_bcast_qdtype":
+    bias = torch.randn(1, H, Nq, Nkv, generator=g).to(torch.bfloat16)
+  elif kind == "key_bias":
+    bias = torch.randn(B, 1, 1, Nkv, generator=g)
+  else:
+    bias = torch.rand(1, 1, Nq, Nkv, generator=g) > 0.3
+    bias[..., 0] = True
+  bias = bias.to(DEV)
+  want_grad = bias.dtype != torch.bool
+  if want_grad:
+    bias.requires_grad_(True)
+  qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+  out = ffpa_attn.ffpa_attn_func(qg, kg, vg, attn_mask=bias)
+  out.backward(d_o)
+  torch.cuda.synchronize()
+  add = torch.where(bias, 0.0, float("-inf")) if bias.dtype == torch.bool else bias.detach().float()
+  rq, rk, rv, rds = orc.attention_bwd(q.cpu(), k.cpu(), v.cpu(), d_o.cpu(), bias=add.cpu().double().numpy())
+  _cmp(qg.grad, rq, 5e-2, "dQ")
+  _cmp(kg.grad, rk, 5e-2, "dK")
+  _cmp(vg.grad, rv, 5e-2, "dV")
+  if want_grad:
+    red = tuple(i for i in range(4) if bias.size(i) == 1 and rds.shape[i] != 1)
+    want = rds.sum(axis=red, keepdims=True) if red else rds
+    assert bias.grad is not None and bias.grad.shape == bias.shape
+    _cmp(bias.grad, want, 5e-2, "dBias")
+
+
+@pytest.mark.parametrize("p_drop", [0.2])
+@pytest.mark.parametrize("causal", [False, True])
+def test_backward_dropout_replay(p_drop, causal):
+  """Dropout replay in the backward (tests/test_ffpa_bwd.py:790-897): the Philox mask of the
+  forward is regenerated from the saved (seed, offset)."""
+  import ffpa_attn
+
+  q, k, v, d_o = _mk(1, 2, 2, 200, 264, 256, torch.float16, seed=6)
+  torch.cuda.manual_seed(1234)
+  seed = int(torch.cuda.initial_seed())
+  offset = int(torch.cuda._get_rng_state_offset())
+  qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+  out = ffpa_attn.ffpa_attn_func(qg, kg, vg, dropout_p=p_drop, is_causal=causal)
+  out.backward(d_o)
+  torch.cuda.synchronize()
+  ro, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), causal=causal, dropout_p=p_drop, philox_seed=seed, philox_offset=offset)
+  assert np.abs(out.detach().float().cpu().numpy() - ro).max() < 4e-2
+  rq, rk, rv, _ = orc.attention_bwd(q.cpu(), k.cpu(), v.cpu(), d_o.cpu(), causal=causal, dropout_p=p_drop,
+                                    philox_seed=seed, philox_offset=offset)
+  _cmp(qg.grad, rq, 2e-2, "dQ")
+  _cmp(kg.grad, rk, 2e-2, "dK")
+  _cmp(vg.grad, rv, 2e-2, "dV")
+
+
 def test_backward_rejects_unsupported():
   import ffpa_attn
 

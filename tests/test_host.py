@@ -62,8 +62,9 @@ int main(void) {
          offsetof(ffpa_fwd_params, batch), offsetof(ffpa_fwd_params, softmax_scale),
          offsetof(ffpa_fwd_params, philox_seed), offsetof(ffpa_fwd_params, philox_offset),
          offsetof(ffpa_fwd_params, workspace_bytes));
-  printf("%zu %zu %zu %zu\n", sizeof(ffpa_bwd_params), offsetof(ffpa_bwd_params, batch),
-         offsetof(ffpa_bwd_params, softmax_scale), offsetof(ffpa_bwd_params, workspace));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ffpa_bwd_params), offsetof(ffpa_bwd_params, batch),
+         offsetof(ffpa_bwd_params, softmax_scale), offsetof(ffpa_bwd_params, workspace),
+         offsetof(ffpa_bwd_params, bias_kind), offsetof(ffpa_bwd_params, d_bias));
   return 0;
 }
 """
@@ -76,7 +77,8 @@ int main(void) {
   F, B = C._FwdParams, C._BwdParams
   want = [ctypes.sizeof(F), F.bias_stride.offset, F.batch.offset, F.softmax_scale.offset,
           F.philox_seed.offset, F.philox_offset.offset, F.workspace_bytes.offset,
-          ctypes.sizeof(B), B.batch.offset, B.softmax_scale.offset, B.workspace.offset]
+          ctypes.sizeof(B), B.batch.offset, B.softmax_scale.offset, B.workspace.offset,
+          B.bias_kind.offset, B.d_bias.offset]
   assert [int(x) for x in out] == want
 
 
