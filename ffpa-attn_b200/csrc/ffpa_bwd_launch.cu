@@ -1,6 +1,7 @@
 // Host launcher of the backward: preprocess (delta, lse2) + dQ + dK + dV kernels on one stream.
 // Implements the symbol the reference leaves as a thrower
 // (/root/reference/csrc/cuffpa/ffpa_api.cc:242-263).
+#include <vector>
 #include "ffpa_internal.h"
 #include "sm100_ptx.cuh"
 
@@ -31,16 +32,47 @@ static bool make_map4(CUtensorMap* m, const void* base, const int64_t* stride, i
   return tmap::encode_sw128(m, const_cast<void*>(base), 2, 4, dims, str, box);
 }
 
+static inline uint64_t align256(uint64_t x) { return (x + 255) / 256 * 256; }
+
+// few KV-stationary items (B*Hkv*ceil(Nkv/128) < 8 clusters' worth): dK/dV may need chunked items
+// with fp32 accumulation buffers; reserve them.
+static bool may_split_kv(int batch, int heads_kv, int seqlen_kv) {
+  const int64_t kv_items = (int64_t)batch * heads_kv * ((seqlen_kv + 127) / 128);
+  return kv_items < 8ll * (sm_count() / 2);
+}
+
 uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
-  (void)heads_kv; (void)seqlen_kv; (void)head_dim;
   const uint64_t nq_pad = ((uint64_t)seqlen_q + 127) / 128 * 128;
-  return 2ull * batch * heads_q * nq_pad * sizeof(float);
+  uint64_t total = align256(2ull * batch * heads_q * nq_pad * sizeof(float));
+  if (may_split_kv(batch, heads_kv, seqlen_kv))
+    total += 2 * align256((uint64_t)batch * heads_kv * seqlen_kv * head_dim * sizeof(float));
+  return total;
+}
+
+template <bool BF16>
+__global__ void f32_to_16_kernel(const float* __restrict__ src, void* __restrict__ dst, int64_t s0, int64_t s1,
+                                 int64_t s2, int H, int N, int D, int64_t total_vec) {
+  // src [B, H, N, D] contiguous fp32 -> dst with element strides (s0, s1, s2, 1); 8 elements per thread
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 8;
+    const int d = (int)(e % D);
+    const int64_t r = e / D;
+    const int n = (int)(r % N);
+    const int h = (int)((r / N) % H);
+    const int64_t b = r / ((int64_t)N * H);
+    const float4 a = *reinterpret_cast<const float4*>(src + e);
+    const float4 c = *reinterpret_cast<const float4*>(src + e + 4);
+    uint4 o;
+    if (BF16) { o.x = ptx::pack_bf16x2(a.x, a.y); o.y = ptx::pack_bf16x2(a.z, a.w); o.z = ptx::pack_bf16x2(c.x, c.y); o.w = ptx::pack_bf16x2(c.z, c.w); }
+    else { o.x = ptx::pack_f16x2(a.x, a.y); o.y = ptx::pack_f16x2(a.z, a.w); o.z = ptx::pack_f16x2(c.x, c.y); o.w = ptx::pack_f16x2(c.z, c.w); }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst) + 2 * (b * s0 + h * s1 + (int64_t)n * s2 + d)) = o;
+  }
 }
 
 int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   const int D = a.head_dim, nqk = (D + 63) / 64;
   const int nq_pad = (a.seqlen_q + 127) / 128 * 128;
-  const uint64_t need = bwd_workspace_bytes(a.batch, a.heads_q, a.heads_kv, a.seqlen_q, a.seqlen_kv, D);
+  const uint64_t need = align256(2ull * a.batch * a.heads_q * nq_pad * sizeof(float));  // lse2 + delta (split buffers optional)
   if (!a.workspace || a.workspace_bytes < need)
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "backward workspace too small: need %llu bytes", (unsigned long long)need);
   float* lse2 = static_cast<float*>(a.workspace);
@@ -59,6 +91,18 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
       !make_map4(&do_km, a.d_o, a.do_stride, B, Hq, Nq, D, 64, 64) || !make_map4(&do_mn, a.d_o, a.do_stride, B, Hq, Nq, D, 64, 128))
     return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed in backward");
 
+  // optional fp32 accumulation buffers for chunked dK / dV items
+  float* dk32 = nullptr;
+  float* dv32 = nullptr;
+  {
+    const uint64_t base = align256(2ull * a.batch * a.heads_q * nq_pad * sizeof(float));
+    const uint64_t one = align256((uint64_t)a.batch * a.heads_kv * a.seqlen_kv * D * sizeof(float));
+    if (may_split_kv(a.batch, a.heads_kv, a.seqlen_kv) && a.workspace_bytes >= base + 2 * one) {
+      dk32 = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + base);
+      dv32 = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + base + one);
+    }
+  }
+
   bwd::BwdKernelParams kp{};
   kp.lse2 = lse2; kp.delta = delta; kp.nq_pad = nq_pad;
   kp.batch = B; kp.heads_q = Hq; kp.heads_kv = Hkv; kp.seqlen_q = Nq; kp.seqlen_kv = Nkv; kp.head_dim = D;
@@ -69,19 +113,83 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   kp.dropout_p = a.dropout_p; kp.philox_seed = a.philox_seed; kp.philox_offset = a.philox_offset;
   kp.dbias = a.d_bias;
   const int max_clusters = sm_count() / 2;
-  auto run = [&](int kind, void* out, const int64_t* ostride, int rows, int heads, const CUtensorMap& a1,
-                 const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2, const CUtensorMap& b3) {
+  const int off = Nkv - Nq;
+  auto run = [&](int kind, void* out, const int64_t* ostride, int rows, int heads, float* acc32,
+                 const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1, const CUtensorMap& b2,
+                 const CUtensorMap& b3) -> int {
     kp.out = out;
     for (int i = 0; i < 3; ++i) kp.out_stride[i] = ostride[i];
     kp.n_rtiles = (rows + 127) / 128;
-    kp.n_items = kp.n_rtiles * B * heads;
+    kp.out_rows = rows;
+    // streamed tiles per item (same rule as col_tiles<KIND> in the kernel)
+    const int group = Hq / Hkv;
+    const int tq = (Nq + 127) / 128, tk = (Nkv + 127) / 128;
+    std::vector<int> tfull(kp.n_rtiles);
+    int tmax = 0;
+    long long tsum = 0;
+    for (int rt = 0; rt < kp.n_rtiles; ++rt) {
+      int t;
+      if (kind == 0) {
+        t = tk;
+        if (a.causal) { const int lim = ((rt * 128 + 127 + off) >> 7) + 1; t = lim < t ? lim : t; }
+        t = t < 1 ? 1 : t;
+      } else {
+        int first = 0;
+        if (a.causal) { const int qmin = rt * 128 - off; first = qmin > 0 ? (qmin >> 7) : 0; first = first > tq ? tq : first; }
+        t = (tq - first) * group;
+      }
+      tfull[rt] = t;
+      tmax = t > tmax ? t : tmax;
+      tsum += t;
+    }
+    const long long nbh = (long long)B * heads;
+    const double avg = (double)tsum * nbh / max_clusters;  // tiles per cluster if perfectly balanced
+    kp.n_chunks = 1;
+    kp.chunk_len = tmax;
+    kp.out32 = nullptr;
+    if (kind != 0 && acc32 != nullptr && tmax > avg / 2) {
+      int len = (int)(avg / 4);
+      len = len < 4 ? 4 : len;
+      if (len < tmax) {
+        kp.chunk_len = len;
+        kp.n_chunks = (tmax + len - 1) / len;
+        kp.out32 = acc32;
+        cudaError_t e = cudaMemsetAsync(acc32, 0, (size_t)B * heads * rows * D * sizeof(float), stream);
+        if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+      }
+    }
+    kp.n_items = kp.n_rtiles * kp.n_chunks * (int)nbh;
     const int ncl = kp.n_items < max_clusters ? kp.n_items : max_clusters;
-    return bf16 ? bwd::dispatch_bwd_dtype<true>(nqk, kind, a1, a2, b1, b2, b3, kp, ncl, stream)
-                : bwd::dispatch_bwd_dtype<false>(nqk, kind, a1, a2, b1, b2, b3, kp, ncl, stream);
+    kp.sched = nullptr;
+    kp.sched_stride = 0;
+    if ((a.causal || kp.n_chunks > 1) && kp.n_items > ncl) {
+      std::vector<int> cost((size_t)kp.n_items);
+      for (int it = 0; it < kp.n_items; ++it) {
+        const int rt = it % kp.n_rtiles;
+        const int chunk = (it / kp.n_rtiles) % kp.n_chunks;
+        int n = tfull[rt] - chunk * kp.chunk_len;
+        n = n < 0 ? 0 : (n < kp.chunk_len ? n : kp.chunk_len);
+        cost[it] = n > 0 ? n * 16 + 24 : 1;
+      }
+      kp.sched = get_schedule(cost.data(), kp.n_items, ncl, &kp.sched_stride, stream);
+    }
+    int r = bf16 ? bwd::dispatch_bwd_dtype<true>(nqk, kind, a1, a2, b1, b2, b3, kp, ncl, stream)
+                 : bwd::dispatch_bwd_dtype<false>(nqk, kind, a1, a2, b1, b2, b3, kp, ncl, stream);
+    if (r) return r;
+    if (kp.out32 != nullptr) {
+      const int64_t total_vec = (int64_t)B * heads * rows * D / 8;
+      const int blocks = (int)((total_vec + 255) / 256 < 4096 ? (total_vec + 255) / 256 : 4096);
+      if (bf16) f32_to_16_kernel<true><<<blocks, 256, 0, stream>>>(acc32, out, ostride[0], ostride[1], ostride[2], heads, rows, D, total_vec);
+      else f32_to_16_kernel<false><<<blocks, 256, 0, stream>>>(acc32, out, ostride[0], ostride[1], ostride[2], heads, rows, D, total_vec);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "fp32->16 convert launch failed: %s", cudaGetErrorString(e));
+      count_launch();
+    }
+    return FFPA_OK;
   };
-  if ((rc = run(0, a.dq, a.dq_stride, Nq, Hq, q_km, do_km, k_km, v_km, k_mn))) return rc;
-  if ((rc = run(1, a.dk, a.dk_stride, Nkv, Hkv, k_km, v_km, q_km, do_km, q_mn))) return rc;
-  if ((rc = run(2, a.dv, a.dv_stride, Nkv, Hkv, k_km, k_km, q_km, q_km, do_mn))) return rc;
+  if ((rc = run(0, a.dq, a.dq_stride, Nq, Hq, nullptr, q_km, do_km, k_km, v_km, k_mn))) return rc;
+  if ((rc = run(1, a.dk, a.dk_stride, Nkv, Hkv, dk32, k_km, v_km, q_km, do_km, q_mn))) return rc;
+  if ((rc = run(2, a.dv, a.dv_stride, Nkv, Hkv, dv32, k_km, k_km, q_km, q_km, do_mn))) return rc;
   return FFPA_OK;
 }
 

@@ -103,6 +103,36 @@ __device__ __forceinline__ TileRange col_tiles(const BwdKernelParams& p, int r0)
   }
 }
 
+// One work item = 128 stationary rows x a contiguous chunk of the streamed (head, column-tile)
+// sequence. With n_chunks > 1 (few, long items: e.g. GQA + causal dK/dV) partial accumulators are
+// added into an fp32 buffer with atomics and converted afterwards.
+struct Item { int rt, bh, s0, n; TileRange tr; };
+
+template <int KIND>
+__device__ __forceinline__ Item decode_item(const BwdKernelParams& p, int item, int n_inner) {
+  Item it;
+  it.rt = item % p.n_rtiles;
+  const int rest = item / p.n_rtiles;
+  const int chunk = rest % p.n_chunks;
+  it.bh = rest / p.n_chunks;
+  it.tr = col_tiles<KIND>(p, it.rt * 128);
+  const int tfull = it.tr.count * n_inner;
+  if (p.n_chunks == 1) { it.s0 = 0; it.n = tfull; }
+  else {
+    it.s0 = chunk * p.chunk_len;
+    int n = tfull - it.s0;
+    n = n < 0 ? 0 : n;
+    it.n = n < p.chunk_len ? n : p.chunk_len;
+  }
+  return it;
+}
+
+__device__ __forceinline__ int next_item(const BwdKernelParams& p, uint32_t cluster, uint32_t nclusters, uint32_t k) {
+  if (p.sched != nullptr) return (k < (uint32_t)p.sched_stride) ? __ldg(p.sched + (size_t)cluster * p.sched_stride + k) : -1;
+  const uint32_t item = cluster + k * nclusters;
+  return item < (uint32_t)p.n_items ? (int)item : -1;
+}
+
 template <int NQK, bool BF16, int KIND, bool GENERAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
@@ -188,13 +218,15 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           ++rc;
         }
       };
-      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
-        const int rt = item % p.n_rtiles;
-        const int bh = item / p.n_rtiles;
+      for (uint32_t kidx = 0;; ++kidx) {
+        const int item_s = next_item(p, cluster, nclusters, kidx);
+        if (item_s < 0) break;
+        const Item itm = decode_item<KIND>(p, item_s, n_inner);
+        const int bh = itm.bh;
         const int hs = bh % heads_it, b = bh / heads_it;  // head of the stationary operand
-        const int r0 = rt * 128;
-        const TileRange tr = col_tiles<KIND>(p, r0);
-        const int T = tr.count * n_inner;
+        const int r0 = itm.rt * 128;
+        const TileRange tr = itm.tr;
+        const int T = itm.n;
         if (T <= 0) continue;
         // stationary operands
         ptx::mbar_wait(bar(bars.a_empty), (it & 1) ^ 1);
@@ -207,13 +239,14 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         }
         for (int step = 0; step <= T; ++step) {
           if (step < T) {
-            const int gi = step / tr.count, ci = tr.first + step % tr.count;
+            const int sa = itm.s0 + step;
+            const int gi = sa / tr.count, ci = tr.first + sa % tr.count;
             const int hb = (KIND == kKindDQ) ? hs / group : hs * group + gi;  // head of the streamed operands
             load_kmajor(&map_b1, ci * 128, hb, b);
             if (HAS_DP) load_kmajor(&map_b2, ci * 128, hb, b);
           }
           if (step >= 1) {
-            const int st = step - 1;
+            const int st = itm.s0 + step - 1;
             const int gi = st / tr.count, ci = tr.first + st % tr.count;
             const int hb = (KIND == kKindDQ) ? hs / group : hs * group + gi;
             load_mnmajor(&map_b3, ci * 128, hb, b);
@@ -249,10 +282,11 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           ++rc;
         }
       };
-      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
-        const int rt = item % p.n_rtiles;
-        const TileRange tr = col_tiles<KIND>(p, rt * 128);
-        const int T = tr.count * n_inner;
+      for (uint32_t kidx = 0;; ++kidx) {
+        const int item_s = next_item(p, cluster, nclusters, kidx);
+        if (item_s < 0) break;
+        const Item itm = decode_item<KIND>(p, item_s, n_inner);
+        const int T = itm.n;
         if (T <= 0) continue;
         ptx::mbar_wait(bar(bars.a_full), it & 1);
         ptx::tc_fence_after();
@@ -303,20 +337,22 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     const uint32_t l_t_full1 = ptx::mapa(bar(bars.t_full[1]), 0);
     const int off = p.seqlen_kv - p.seqlen_q;
     uint32_t g = 0;
-    for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
-      const int rt = item % p.n_rtiles;
-      const int bh = item / p.n_rtiles;
+    for (uint32_t kidx = 0;; ++kidx) {
+      const int item_s = next_item(p, cluster, nclusters, kidx);
+      if (item_s < 0) break;
+      const Item itm = decode_item<KIND>(p, item_s, n_inner);
+      const int bh = itm.bh;
       const int hs = bh % heads_it, b = bh / heads_it;
-      const int r0 = rt * 128;
-      const TileRange tr = col_tiles<KIND>(p, r0);
-      const int T = tr.count * n_inner;
+      const int r0 = itm.rt * 128;
+      const TileRange tr = itm.tr;
+      const int T = itm.n;
       const int grow = r0 + 64 * (int)rank + (int)row;  // global stationary row (query or key)
       const bool row_ok = grow < ((KIND == kKindDQ) ? p.seqlen_q : p.seqlen_kv);
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
                       2 * ((int64_t)b * p.out_stride[0] + (int64_t)hs * p.out_stride[1] + (int64_t)grow * p.out_stride[2]);
       if (T <= 0) {
-        // nothing contributes (causal, keys beyond every query's window): gradient is zero
-        if (row_ok) {
+        // nothing contributes: gradient is zero (already so in the pre-zeroed fp32 buffer of split mode)
+        if (row_ok && p.out32 == nullptr) {
           for (int d = (int)(kh * 2 + ch) * 8; d < p.head_dim; d += 32)
             *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(0, 0, 0, 0);
         }
@@ -330,7 +366,8 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       }
       for (int i = 0; i < T; ++i, ++g) {
         const uint32_t sbuf = g & 1;
-        const int gi = i / tr.count, ci = tr.first + i % tr.count;
+        const int sa = itm.s0 + i;
+        const int gi = sa / tr.count, ci = tr.first + sa % tr.count;
         const int col0 = ci * 128 + 64 * (int)kh + 32 * (int)ch;  // first global column of this thread
         // column statistics (dK / dV kinds): issue the loads before waiting for the MMA
         float4 c_lse[8], c_dl[8];
@@ -447,7 +484,13 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           ptx::tmem_ld_x32(tmem + lane_base + 64 * s + 32 * ch, orr);
           ptx::tmem_wait_ld();
           const int d0 = 128 * s + 64 * (int)kh + 32 * (int)ch;
-          if (row_ok) {
+          if (row_ok && p.out32 != nullptr) {
+            // split mode: accumulate this chunk's partial result (fp32, [B, H, rows, D] contiguous)
+            float* dst = p.out32 + (((int64_t)b * heads_it + hs) * p.out_rows + grow) * (int64_t)p.head_dim;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (d0 + j < p.head_dim) atomicAdd(dst + d0 + j, __uint_as_float(orr[j]) * mulo);
+          } else if (row_ok) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               const int d = d0 + 8 * v;

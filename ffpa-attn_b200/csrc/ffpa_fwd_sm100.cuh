@@ -49,14 +49,19 @@ struct FwdCfg {
   static constexpr int KST = (NQK + 1) / 2;               // 16 KB K stages per KV tile
   static constexpr int S_BASE = O_COLS > 256 ? 384 : 256; // TMEM column of S[0]; S[1] = +64
   static constexpr int Q_BYTES = NQK * 8192;
-  static constexpr int P_BYTES = 2 * 16384;
-  static constexpr int NVS = HD > 768 ? 1 : (HD > 256 ? 2 : 3);  // 32 KB V stages
+  // depth of the S (TMEM) / P (SMEM) pipeline = tiles whose softmax may be in flight. The
+  // S -> softmax -> P -> PV chain costs ~2000 cycles of latency per tile; with depth k the tensor
+  // pipe stays busy when (T_mma + 2000) / k <= T_mma, i.e. k = 2 suffices at D = 512 (T_mma = 2048)
+  // but small heads need 3-4 (TMEM: O_COLS + 64 k <= 512).
+  static constexpr int KSTG = HD <= 256 ? 4 : (HD <= 384 ? 3 : 2);
+  static constexpr int P_BYTES = KSTG * 16384;
+  static constexpr int NVS = HD > 768 ? 1 : 2;  // 32 KB V stages
   static constexpr int kBudget = kSmemLimit - 3072;  // static smem (barriers + exchange), 1 KB aligned
   static constexpr int kNksRaw = (kBudget - Q_BYTES - P_BYTES - NVS * 32768) / 16384;
   static constexpr int NKS = kNksRaw > 8 ? 8 : kNksRaw;   // 16 KB K stages
   static constexpr int SMEM_DYN = Q_BYTES + P_BYTES + NKS * 16384 + NVS * 32768;
   static_assert(NKS >= 2, "not enough shared memory for the K ring");
-  static_assert(O_COLS + 128 <= 512 && S_BASE >= O_COLS, "O does not fit TMEM next to S");
+  static_assert(S_BASE + 64 * KSTG <= 512 && S_BASE >= O_COLS, "O does not fit TMEM next to S");
   // width of the O slab of pass `pass`, and N of its slice s
   __host__ __device__ static constexpr int slab_w(int pass) { return (DVP - pass * DSLAB) >= DSLAB ? DSLAB : (DVP - pass * DSLAB); }
   __host__ __device__ static constexpr int slice_n(int w, int s) { return (w - 256 * s) >= 256 ? 256 : 128; }
@@ -66,8 +71,8 @@ struct Barriers {
   uint64_t q_full, q_empty;
   uint64_t k_full[8], k_empty[8];
   uint64_t v_full[3], v_empty[3];
-  uint64_t s_full[2];
-  uint64_t p_full[2], p_empty[2];
+  uint64_t s_full[4];
+  uint64_t p_full[4], p_empty[4];
 };
 
 __device__ __forceinline__ int num_kv_tiles(const FwdKernelParams& p, int q0) {
@@ -132,6 +137,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const __grid_constant__ CUtensorMap map_v, const FwdKernelParams p) {
   using Cfg = FwdCfg<NQK>;
   constexpr int CG = 2;
+  constexpr uint32_t KS = Cfg::KSTG;   // S/P pipeline depth
+  constexpr int LA = Cfg::KSTG - 1;    // QK runs LA tiles ahead of PV
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ Barriers bars;
   __shared__ float xch[2][4][64];  // per-tile row-max exchange: [S stage][kh*2+ch][row]
@@ -156,7 +163,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     ptx::mbar_init(bar(bars.q_empty), 1);
     for (int i = 0; i < 8; ++i) { ptx::mbar_init(bar(bars.k_full[i]), 1); ptx::mbar_init(bar(bars.k_empty[i]), 1); }
     for (int i = 0; i < 3; ++i) { ptx::mbar_init(bar(bars.v_full[i]), 1); ptx::mbar_init(bar(bars.v_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(bar(bars.s_full[i]), 1);
       ptx::mbar_init(bar(bars.p_full[i]), 2 * kSoftmaxWarps);  // softmax warps of both CTAs
       ptx::mbar_init(bar(bars.p_empty[i]), 1);
@@ -201,7 +208,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
         for (int jb = 0; jb < NQK; ++jb)
           ptx::tma_load_4d_2sm(sQ + jb * 8192, &map_q, l_q_full, jb * 64, q0 + 64 * (int)rank, h, b);
-        for (int step = 0; step <= T; ++step) {
+        for (int step = 0; step < T + LA; ++step) {
           if (step < T) {
             const int kv0 = step * 128;
 #pragma unroll
@@ -217,8 +224,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               ++kc;
             }
           }
-          if (step >= 1) {
-            const int kv0 = (step - 1) * 128;
+          if (step >= LA) {
+            const int kv0 = (step - LA) * 128;
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
               if (256 * s >= dvw) break;
@@ -254,9 +261,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int T = num_kv_tiles(p, mt * 128);
         ptx::mbar_wait(bar(bars.q_full), it & 1);
         ptx::tc_fence_after();
-        for (int step = 0; step <= T; ++step) {
+        for (int step = 0; step < T + LA; ++step) {
           if (step < T) {
-            const uint32_t sbuf = g & 1;
+            const uint32_t sbuf = g % KS;
             const uint32_t d_tmem = tmem + Cfg::S_BASE + 64 * sbuf;
 #pragma unroll
             for (int ks = 0; ks < Cfg::KST; ++ks) {
@@ -279,9 +286,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             if (step == T - 1) ptx::umma_commit_mc<CG>(bar(bars.q_empty), 0x3);
             ++g;
           }
-          if (step >= 1) {
-            const uint32_t pbuf = gp & 1;
-            ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp >> 1) & 1);
+          if (step >= LA) {
+            const uint32_t pbuf = gp % KS;
+            ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp / KS) & 1);
             ptx::tc_fence_after();
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
@@ -295,7 +302,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               for (int kk = 0; kk < 8; ++kk) {
                 const uint64_t ad = ptx::make_smem_desc_sw128(sP + pbuf * 16384 + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
                 const uint64_t bd = ptx::make_smem_desc_sw128(sV + stage * 32768 + kk * 2048, 16384, 1024);
-                ptx::umma_f16_ss<CG>(tmem + 128 * s, ad, bd, idesc_pv, (step > 1 || kk > 0) ? 1u : 0u);
+                ptx::umma_f16_ss<CG>(tmem + 128 * s, ad, bd, idesc_pv, (step > LA || kk > 0) ? 1u : 0u);
               }
               ptx::umma_commit_mc<CG>(bar(bars.v_empty[stage]), 0x3);
               ++vc;
@@ -319,7 +326,6 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t rgrp = warp & 1;           // warps sharing rows: {0,2,4,6} / {1,3,5,7}
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;
     const uint32_t l_p_full0 = ptx::mapa(bar(bars.p_full[0]), 0);
-    const uint32_t l_p_full1 = ptx::mapa(bar(bars.p_full[1]), 0);
     const float NEG_INF = -INFINITY;
     // softmax domain: fast mode works on raw scores (mul = scale*log2e), general on scaled+biased
     const float mul = (MODE == kModeFast) ? p.scale_log2 : 1.0f;
@@ -340,8 +346,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       float m = NEG_INF, l = 0.f;
 
       for (int i = 0; i < T; ++i, ++g) {
-        const uint32_t sbuf = g & 1;
-        ptx::mbar_wait(bar(bars.s_full[sbuf]), (g >> 1) & 1);
+        const uint32_t sbuf = g % KS;   // S / P pipeline stage
+        const uint32_t xb = g & 1;      // row-max exchange buffer
+        ptx::mbar_wait(bar(bars.s_full[sbuf]), (g / KS) & 1);
         ptx::tc_fence_after();
         uint32_t sr[32];
         ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32 * ch, sr);
@@ -388,9 +395,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         mx2 = fmax3(mx2, x[24], x[25]); mx3 = fmax3(mx3, x[26], x[27]);
         mx0 = fmax3(mx0, x[28], x[29]); mx1 = fmax3(mx1, x[30], x[31]);
         float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3);
-        xch[sbuf][slot][row] = tmax;
+        xch[xb][slot][row] = tmax;
         ptx::named_bar_sync(1 + rgrp, 128);
-        tmax = fmaxf(fmax3(xch[sbuf][0][row], xch[sbuf][1][row], xch[sbuf][2][row]), xch[sbuf][3][row]);
+        tmax = fmaxf(fmax3(xch[xb][0][row], xch[xb][1][row], xch[xb][2][row]), xch[xb][3][row]);
         // lazy rescale: keep the stale max while the true max is < 8 (log2 units) above it
         // (/root/reference/csrc/cuffpa/native/prefill.cuh:719-738, common.cuh:14-18)
         const float m_new = fmaxf(m, tmax);
@@ -448,7 +455,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         m = m_use;
 
         // P buffer free? (PV of tile g-2 retired)
-        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((g >> 1) & 1) ^ 1);
+        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((g / KS) & 1) ^ 1);
         {
           const uint32_t prow = sP + sbuf * 16384 + kh * 8192 + row * 128;
 #pragma unroll
@@ -461,7 +468,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         if (__any_sync(0xffffffffu, need_rescale)) {
           // O may only be touched once PV of tile g-1 has retired; each warpgroup scales half the columns
-          ptx::mbar_wait(bar(bars.p_empty[(g - 1) & 1]), ((g - 1) >> 1) & 1);
+          ptx::mbar_wait(bar(bars.p_empty[(g - 1) % KS]), ((g - 1) / KS) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
           for (int c0 = (int)ch * (dvw / 4); c0 < (int)(ch + 1) * (dvw / 4); c0 += 32) {
@@ -477,13 +484,13 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
-        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(sbuf ? l_p_full1 : l_p_full0);
+        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(l_p_full0 + 8u * sbuf);  // p_full[] is contiguous
       }
 
       // ---------------- epilogue: O / l -> global, LSE ----------------
       {
         const uint32_t gl = g - 1;
-        ptx::mbar_wait(bar(bars.p_empty[gl & 1]), (gl >> 1) & 1);
+        ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
         ptx::tc_fence_after();
         // row-sum exchange reuses the max-exchange buffer of the last tile: every thread of the
         // row group finished reading it before PV(gl) could retire (p_full precedes p_empty).

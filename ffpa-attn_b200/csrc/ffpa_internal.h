@@ -45,6 +45,12 @@ struct BwdKernelParams {
   float dropout_p;
   uint64_t philox_seed, philox_offset;
   float* dbias;
+  // scheduling: optional balanced table (as in the forward) and chunked items with fp32 atomics
+  const int* sched;
+  int sched_stride;
+  int n_chunks, chunk_len;
+  float* out32;   // non-null: accumulate into fp32 [B, H, out_rows, D] instead of storing `out`
+  int out_rows;
 };
 }  // namespace bwd
 
