@@ -25,10 +25,6 @@
 
 namespace ffpa {
 
-constexpr int kSoftmaxWarps = 8;
-constexpr int kMmaWarp = 8;
-constexpr int kTmaWarp = 9;
-constexpr int kThreads = 320;
 constexpr int kSmemLimit = 232448;
 
 // softmax flavour
@@ -54,9 +50,20 @@ struct FwdCfg {
   // pipe stays busy when (T_mma + 2000) / k <= T_mma, i.e. k = 2 suffices at D = 512 (T_mma = 2048)
   // but small heads need 3-4 (TMEM: O_COLS + 64 k <= 512).
   static constexpr int KSTG = HD <= 256 ? 4 : (HD <= 384 ? 3 : 2);
+  // softmax warps: 8 (two per scheduler, each thread owns 32 keys of a row) when the tensor pipe is the
+  // limiter, 16 (four per scheduler, 16 keys per thread) for small heads where the SIMT side is
+  // (profiles/r01_fwd_small_d_ncu.md)
+  // Measured (profiles/r01_fwd_timings_v5.log): 16 warps are 5-8 % SLOWER at D <= 256 than 8 -- the SIMT
+  // limit there is pipe throughput (MUFU.EX2 + conversions), not latency hiding -- so 8 is used everywhere;
+  // the kernel stays generic in NSW.
+  static constexpr int NSW = 8;
+  static constexpr int CQ = NSW / 4;        // column groups of the 64-column S stage
+  static constexpr int CPT = 64 / CQ;       // S columns (keys) per thread and tile
+  static constexpr int MMA_WARP = NSW, TMA_WARP = NSW + 1;
+  static constexpr int THREADS = (NSW + 2) * 32;
   static constexpr int P_BYTES = KSTG * 16384;
   static constexpr int NVS = HD > 768 ? 1 : 2;  // 32 KB V stages
-  static constexpr int kBudget = kSmemLimit - 3072;  // static smem (barriers + exchange), 1 KB aligned
+  static constexpr int kBudget = kSmemLimit - (NSW == 16 ? 5120 : 3072);  // static smem (barriers + exchange), 1 KB aligned
   static constexpr int kNksRaw = (kBudget - Q_BYTES - P_BYTES - NVS * 32768) / 16384;
   static constexpr int NKS = kNksRaw > 8 ? 8 : kNksRaw;   // 16 KB K stages
   static constexpr int SMEM_DYN = Q_BYTES + P_BYTES + NKS * 16384 + NVS * 32768;
@@ -132,7 +139,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 
 template <int NQK, bool BF16, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FwdCfg<NQK>::THREADS, 1)
 ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const FwdKernelParams p) {
   using Cfg = FwdCfg<NQK>;
@@ -141,7 +148,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   constexpr int LA = Cfg::KSTG - 1;    // QK runs LA tiles ahead of PV
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ Barriers bars;
-  __shared__ float xch[2][4][64];  // per-tile row-max exchange: [S stage][kh*2+ch][row]
+  constexpr int kMmaWarp = Cfg::MMA_WARP, kTmaWarp = Cfg::TMA_WARP, kSoftmaxWarps = Cfg::NSW;
+  constexpr int CQ = Cfg::CQ, CPT = Cfg::CPT;
+  __shared__ float xch[2][2 * Cfg::CQ][64];  // per-tile row-max exchange: [parity][kh*CQ+ch][row]
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
@@ -316,13 +325,13 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     __syncwarp();
   } else {
     // =========================================== softmax / correction / epilogue ================
-    // 256 threads: TMEM lane = t % 128; warpgroup ch = t / 128 owns S columns [32ch, 32ch+32).
+    // NSW*32 threads: TMEM lane = t % 128; warpgroup ch = t / 128 owns S columns [CPT*ch, CPT*ch+CPT).
     const uint32_t t = threadIdx.x;
     const uint32_t lane128 = t & 127;
     const uint32_t row = lane128 & 63;        // row inside this CTA's 64
     const uint32_t kh = lane128 >> 6;         // 64-key half of the KV tile / column half of O
     const uint32_t ch = t >> 7;               // column half inside the S stage
-    const uint32_t slot = kh * 2 + ch;
+    const uint32_t slot = kh * CQ + ch;
     const uint32_t rgrp = warp & 1;           // warps sharing rows: {0,2,4,6} / {1,3,5,7}
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;
     const uint32_t l_p_full0 = ptx::mapa(bar(bars.p_full[0]), 0);
@@ -350,23 +359,24 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t xb = g & 1;      // row-max exchange buffer
         ptx::mbar_wait(bar(bars.s_full[sbuf]), (g / KS) & 1);
         ptx::tc_fence_after();
-        uint32_t sr[32];
-        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32 * ch, sr);
+        uint32_t sr[CPT];
+        if constexpr (CPT == 32) ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + CPT * ch, sr);
+        else ptx::tmem_ld_x16(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + CPT * ch, sr);
         ptx::tmem_wait_ld();
-        float x[32];
-        const int key0 = i * 128 + 64 * (int)kh + 32 * (int)ch;
+        float x[CPT];
+        const int key0 = i * 128 + 64 * (int)kh + CPT * (int)ch;
         if constexpr (MODE == kModeFast) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]);
+          for (int j = 0; j < CPT; ++j) x[j] = __uint_as_float(sr[j]);
         } else {
           if (p.bias_kind == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]) * p.scale_log2;
+            for (int j = 0; j < CPT; ++j) x[j] = __uint_as_float(sr[j]) * p.scale_log2;
           } else {
             const int64_t boff = (int64_t)b * p.bias_stride[0] + (int64_t)h * p.bias_stride[1] +
                                  (int64_t)(gq < p.seqlen_q ? gq : 0) * p.bias_stride[2];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < CPT; ++j) {
               const int key = key0 + j;
               float bv = 0.f;
               if (key < p.seqlen_kv) {
@@ -383,21 +393,25 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (tail || diag) {
           const int lim = p.causal ? (causal_lim < p.seqlen_kv - 1 ? causal_lim : p.seqlen_kv - 1) : p.seqlen_kv - 1;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < CPT; ++j)
             if (key0 + j > lim) x[j] = NEG_INF;
         }
-        // local max: 4 independent chains of 3-input max
+        // local max: independent chains of 3-input max
         float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
         float mx2 = fmax3(x[6], x[7], x[8]), mx3 = fmax3(x[9], x[10], x[11]);
         mx0 = fmax3(mx0, x[12], x[13]); mx1 = fmax3(mx1, x[14], x[15]);
-        mx2 = fmax3(mx2, x[16], x[17]); mx3 = fmax3(mx3, x[18], x[19]);
-        mx0 = fmax3(mx0, x[20], x[21]); mx1 = fmax3(mx1, x[22], x[23]);
-        mx2 = fmax3(mx2, x[24], x[25]); mx3 = fmax3(mx3, x[26], x[27]);
-        mx0 = fmax3(mx0, x[28], x[29]); mx1 = fmax3(mx1, x[30], x[31]);
+        if constexpr (CPT == 32) {
+          mx2 = fmax3(mx2, x[16], x[17]); mx3 = fmax3(mx3, x[18], x[19]);
+          mx0 = fmax3(mx0, x[20], x[21]); mx1 = fmax3(mx1, x[22], x[23]);
+          mx2 = fmax3(mx2, x[24], x[25]); mx3 = fmax3(mx3, x[26], x[27]);
+          mx0 = fmax3(mx0, x[28], x[29]); mx1 = fmax3(mx1, x[30], x[31]);
+        }
         float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3);
         xch[xb][slot][row] = tmax;
-        ptx::named_bar_sync(1 + rgrp, 128);
+        ptx::named_bar_sync(1 + rgrp, kSoftmaxWarps * 16);
         tmax = fmaxf(fmax3(xch[xb][0][row], xch[xb][1][row], xch[xb][2][row]), xch[xb][3][row]);
+        if constexpr (CQ == 4)
+          tmax = fmaxf(tmax, fmaxf(fmax3(xch[xb][4][row], xch[xb][5][row], xch[xb][6][row]), xch[xb][7][row]));
         // lazy rescale: keep the stale max while the true max is < 8 (log2 units) above it
         // (/root/reference/csrc/cuffpa/native/prefill.cuh:719-738, common.cuh:14-18)
         const float m_new = fmaxf(m, tmax);
@@ -408,7 +422,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const float neg_mc = -m_safe * mul;
         float factor = 1.f;
         if (need_rescale) factor = exp2f((m - m_use) * mul);
-        uint32_t pk[16];
+        uint32_t pk[CPT / 2];
         float lsum;
         if constexpr (MODE == kModeDropout) {
           // keep iff u > p; the row sum uses the un-dropped probabilities
@@ -419,7 +433,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               (uint64_t)key0;
           lsum = 0.f;
 #pragma unroll
-          for (int j2 = 0; j2 < 32; j2 += 2) {
+          for (int j2 = 0; j2 < CPT; j2 += 2) {
             float pv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -438,7 +452,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const float2 mul2 = make_float2(mul, mul), nm2 = make_float2(neg_mc, neg_mc);
           float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < CPT; j += 4) {
             const float2 a0 = ffma2(make_float2(x[j], x[j + 1]), mul2, nm2);
             const float2 a1 = ffma2(make_float2(x[j + 2], x[j + 3]), mul2, nm2);
             const float2 e0 = make_float2(exp2f(a0.x), exp2f(a0.y));
@@ -459,8 +473,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         {
           const uint32_t prow = sP + sbuf * 16384 + kh * 8192 + row * 128;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t addr = prow + (((4 * ch + c) ^ (row & 7)) << 4);
+          for (int c = 0; c < CPT / 8; ++c) {
+            const uint32_t addr = prow + ((((CPT / 8) * ch + c) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
                          "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
                          : "memory");
@@ -471,13 +485,15 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           ptx::mbar_wait(bar(bars.p_empty[(g - 1) % KS]), ((g - 1) / KS) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int c0 = (int)ch * (dvw / 4); c0 < (int)(ch + 1) * (dvw / 4); c0 += 32) {
-            uint32_t orr[32];
-            ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
+          for (int c0 = (int)ch * (dvw / 2 / CQ); c0 < (int)(ch + 1) * (dvw / 2 / CQ); c0 += CPT) {
+            uint32_t orr[CPT];
+            if constexpr (CPT == 32) ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
+            else ptx::tmem_ld_x16(tmem + lane_base + c0, orr);
             ptx::tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * factor);
-            ptx::tmem_st_x32(tmem + lane_base + c0, orr);
+            for (int j = 0; j < CPT; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * factor);
+            if constexpr (CPT == 32) ptx::tmem_st_x32(tmem + lane_base + c0, orr);
+            else ptx::tmem_st_x16(tmem + lane_base + c0, orr);
           }
           ptx::tmem_wait_st();
         }
@@ -496,8 +512,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // row group finished reading it before PV(gl) could retire (p_full precedes p_empty).
         float (*xl)[64] = xch[gl & 1];
         xl[slot][row] = l;
-        ptx::named_bar_sync(1 + rgrp, 128);
-        const float l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
+        ptx::named_bar_sync(1 + rgrp, kSoftmaxWarps * 16);
+        float l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
+        if constexpr (CQ == 4) l_tot += (xl[4][row] + xl[5][row]) + (xl[6][row] + xl[7][row]);
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
         const bool row_ok = gq < p.seqlen_q;
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
@@ -506,16 +523,17 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int s = 0; s < Cfg::NSLICE; ++s) {
           if (256 * s >= dvw) break;
           const int ns = Cfg::slice_n(dvw, s);
-          const int half = ns / 4;  // columns of this slice handled by each warpgroup
+          const int part = ns / 2 / CQ;  // columns of this slice handled by each warpgroup
 #pragma unroll 1
-          for (int c0 = (int)ch * half; c0 < (int)(ch + 1) * half; c0 += 32) {
-            uint32_t orr[32];
-            ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
+          for (int c0 = (int)ch * part; c0 < (int)(ch + 1) * part; c0 += CPT) {
+            uint32_t orr[CPT];
+            if constexpr (CPT == 32) ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
+            else ptx::tmem_ld_x16(tmem + lane_base + 128 * s + c0, orr);
             ptx::tmem_wait_ld();
             const int d0 = dv0 + 256 * s + (ns / 2) * (int)kh + c0;
             if (row_ok) {
 #pragma unroll
-              for (int v = 0; v < 4; ++v) {
+              for (int v = 0; v < CPT / 8; ++v) {
                 const int d = d0 + 8 * v;
                 if (d < p.head_dim) {
                   uint32_t w[4];
@@ -560,7 +578,7 @@ static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CU
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
     attr_set = true;
   }
-  kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
+  kern<<<dim3(2 * nclusters), dim3(Cfg::THREADS), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "forward launch failed: %s", cudaGetErrorString(e));
   count_launch();
