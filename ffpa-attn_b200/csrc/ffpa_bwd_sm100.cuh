@@ -577,11 +577,15 @@ static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, cons
                               int nclusters, cudaStream_t stream) {
   using Cfg = BwdCfg<NQK, KIND>;
   auto kern = ffpa_bwd_kernel<NQK, BF16, KIND, GENERAL>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in shared-memory size is a per-device function attribute
+  static bool attr_set[64] = {};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  dev_id = (dev_id >= 0 && dev_id < 64) ? dev_id : 0;
+  if (!attr_set[dev_id]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN);
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(bwd smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev_id] = true;
   }
   kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(a1, a2, b1, b2, b3, kp);
   cudaError_t e = cudaGetLastError();

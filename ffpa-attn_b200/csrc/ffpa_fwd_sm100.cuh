@@ -572,11 +572,15 @@ static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CU
                           const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
   using Cfg = FwdCfg<NQK>;
   auto kern = ffpa_fwd_kernel<NQK, BF16, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in shared-memory size is a per-device function attribute
+  static bool attr_set[64] = {};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  dev_id = (dev_id >= 0 && dev_id < 64) ? dev_id : 0;
+  if (!attr_set[dev_id]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN);
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev_id] = true;
   }
   kern<<<dim3(2 * nclusters), dim3(Cfg::THREADS), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
   cudaError_t e = cudaGetLastError();

@@ -4,11 +4,12 @@ Importing this package loads ``libffpa_b200.so`` (hand-written sm_100a kernels b
 ``include/ffpa_b200.h``) and registers ``torch.ops.ffpa_attn._fwd_cuda`` / ``_bwd_cuda``.
 """
 from .cuda import CudaBackendImpl, get_cuda_backend_impl, set_cuda_backend_impl
-from .ffpa_attn_interface import ffpa_attn_func
+from .ffpa_attn_interface import ffpa_attn_func, ffpa_attn_varlen_func
 from .functional import CUDABackend, FFPAAttnFunc, FFPAAttnMeta
 
 __all__ = [
   "ffpa_attn_func",
+  "ffpa_attn_varlen_func",
   "CUDABackend",
   "FFPAAttnFunc",
   "FFPAAttnMeta",

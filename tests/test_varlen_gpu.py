@@ -1,0 +1,71 @@
+"""GPU tests of the packed-THD varlen entry (reference API: ffpa_attn_interface.py:192-279; semantics
+cute/__init__.py:466-571: per-sequence lower-right causal, LSE [Hq, T_q])."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _pack(lens_q, lens_k, Hq, Hkv, D, dtype, seed=0):
+  torch.manual_seed(seed)
+  cq = torch.tensor([0] + list(np.cumsum(lens_q)), dtype=torch.int32, device=DEV)
+  ck = torch.tensor([0] + list(np.cumsum(lens_k)), dtype=torch.int32, device=DEV)
+  q = torch.randn(int(cq[-1]), Hq, D).to(dtype).to(DEV)
+  k = torch.randn(int(ck[-1]), Hkv, D).to(dtype).to(DEV)
+  v = torch.randn(int(ck[-1]), Hkv, D).to(dtype).to(DEV)
+  return q, k, v, cq, ck
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("D", [128, 512])
+def test_varlen_forward_lse_and_backward(causal, D):
+  import ffpa_attn
+
+  lens_q, lens_k = [130, 1, 257, 64], [200, 77, 257, 300]
+  q, k, v, cq, ck = _pack(lens_q, lens_k, 4, 2, D, torch.bfloat16)
+  out, lse = ffpa_attn.ffpa_attn_varlen_func(q, k, v, cq, ck, max(lens_q), max(lens_k), causal=causal,
+                                             enable_gqa=True, return_lse=True)
+  assert out.shape == q.shape and lse.shape == (4, q.size(0)) and lse.dtype == torch.float32
+  qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+  d_o = torch.randn_like(q)
+  og = ffpa_attn.ffpa_attn_varlen_func(qg, kg, vg, cq, ck, max(lens_q), max(lens_k), causal=causal, enable_gqa=True)
+  og.backward(d_o)
+  torch.cuda.synchronize()
+  cql, ckl = cq.tolist(), ck.tolist()
+  for b in range(len(lens_q)):
+    sq, sk = slice(cql[b], cql[b + 1]), slice(ckl[b], ckl[b + 1])
+    qb = q[sq].transpose(0, 1)[None].cpu()
+    kb, vb = k[sk].transpose(0, 1)[None].cpu(), v[sk].transpose(0, 1)[None].cpu()
+    ref, lref = orc.attention_fwd(qb, kb, vb, causal=causal)
+    got = out[sq].transpose(0, 1)[None].float().cpu().numpy()
+    assert np.abs(got - ref).max() < 2e-2
+    assert np.abs(lse[:, sq].cpu().numpy() - lref[0]).max() < 2e-3
+    assert np.abs(og[sq].transpose(0, 1)[None].detach().float().cpu().numpy() - ref).max() < 2e-2
+    dob = d_o[sq].transpose(0, 1)[None].cpu()
+    rq, rk, rv, _ = orc.attention_bwd(qb, kb, vb, dob, causal=causal)
+    for got_g, want in ((qg.grad[sq].transpose(0, 1)[None], rq), (kg.grad[sk].transpose(0, 1)[None], rk),
+                        (vg.grad[sk].transpose(0, 1)[None], rv)):
+      err = np.abs(got_g.float().cpu().numpy() - want).max()
+      assert err < 1e-1 * max(1.0, np.abs(want).max())
+
+
+def test_varlen_validation_errors():
+  import ffpa_attn
+
+  q, k, v, cq, ck = _pack([64, 64], [64, 64], 2, 2, 64, torch.bfloat16)
+  with pytest.raises(TypeError):
+    ffpa_attn.ffpa_attn_varlen_func(q, k, v, cq.long(), ck, 64, 64)
+  with pytest.raises(NotImplementedError):
+    ffpa_attn.ffpa_attn_varlen_func(q, k, v, cq, ck, 64, 64, dropout_p=0.1)
+  with pytest.raises(NotImplementedError):
+    ffpa_attn.ffpa_attn_varlen_func(q, k, v, cq, ck, 64, 64, window_size=(8, 8))
+  with pytest.raises(ValueError):
+    ffpa_attn.ffpa_attn_varlen_func(q, k[:, :1], v[:, :1], cq, ck, 64, 64)
+  bad = cq.clone()
+  bad[-1] += 1
+  with pytest.raises(ValueError):
+    ffpa_attn.ffpa_attn_varlen_func(q, k, v, bad, ck, 64, 64)
