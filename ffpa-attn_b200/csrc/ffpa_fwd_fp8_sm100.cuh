@@ -55,7 +55,8 @@ struct Fp8Cfg {
   static constexpr int KST = (NB + 1) / 2;         // 16 KB K stages ([64 keys x 256 d]) per KV tile
   static constexpr int S_BASE = 256;
   static constexpr int Q_BYTES = NB * 8192;
-  static constexpr int P_BYTES = 2 * 8192;
+  static constexpr int KSTG = HD <= 256 ? 4 : 2;   // S (TMEM) / P (SMEM) pipeline depth
+  static constexpr int P_BYTES = KSTG * 8192;
   static constexpr int kBudget = kSmemLimit - 3072;
   static constexpr int kAvail = (kBudget - Q_BYTES - P_BYTES) / 16384;
   static constexpr int NVS = (kAvail / 2) > 6 ? 6 : (kAvail / 2);    // 16 KB V stages ([128 keys x 128 d])
@@ -69,8 +70,8 @@ struct Barriers {
   uint64_t q_full, q_empty;
   uint64_t k_full[8], k_empty[8];
   uint64_t v_full[6], v_empty[6];
-  uint64_t s_full[2];
-  uint64_t p_full[2], p_empty[2];
+  uint64_t s_full[4];
+  uint64_t p_full[4], p_empty[4];
 };
 
 __device__ __forceinline__ int num_kv_tiles(const Fp8KernelParams& p, int q0) {
@@ -86,6 +87,21 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)),
+        "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
 }
 // two floats -> two e4m3 bytes (lo at the lower address)
 __device__ __forceinline__ uint32_t pack_e4m3x2(float lo, float hi) {
@@ -103,6 +119,8 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const __grid_constant__ CUtensorMap map_v, const Fp8KernelParams p) {
   using Cfg = Fp8Cfg<NB>;
   constexpr int CG = 2;
+  constexpr uint32_t KS = Cfg::KSTG;
+  constexpr int LA = Cfg::KSTG - 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ Barriers bars;
   __shared__ float xch[2][4][64];
@@ -126,7 +144,7 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     ptx::mbar_init(bar(bars.q_empty), 1);
     for (int i = 0; i < 8; ++i) { ptx::mbar_init(bar(bars.k_full[i]), 1); ptx::mbar_init(bar(bars.k_empty[i]), 1); }
     for (int i = 0; i < 6; ++i) { ptx::mbar_init(bar(bars.v_full[i]), 1); ptx::mbar_init(bar(bars.v_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(bar(bars.s_full[i]), 1);
       ptx::mbar_init(bar(bars.p_full[i]), 2 * kSoftmaxWarps);
       ptx::mbar_init(bar(bars.p_empty[i]), 1);
@@ -165,7 +183,7 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb)
           ptx::tma_load_4d_2sm(sQ + jb * 8192, &map_q, l_q_full, jb * 128, q0 + 64 * (int)rank, h, b);
-        for (int step = 0; step <= T; ++step) {
+        for (int step = 0; step < T + LA; ++step) {
           if (step < T) {
             const int kv0 = step * 128;
 #pragma unroll
@@ -181,8 +199,8 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               ++kc;
             }
           }
-          if (step >= 1) {
-            const int kv0 = (step - 1) * 128;
+          if (step >= LA) {
+            const int kv0 = (step - LA) * 128;
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
               const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
@@ -208,9 +226,9 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const int T = num_kv_tiles(p, mt * 128);
         ptx::mbar_wait(bar(bars.q_full), it & 1);
         ptx::tc_fence_after();
-        for (int step = 0; step <= T; ++step) {
+        for (int step = 0; step < T + LA; ++step) {
           if (step < T) {
-            const uint32_t sbuf = g & 1;
+            const uint32_t sbuf = g % KS;
             const uint32_t d_tmem = tmem + Cfg::S_BASE + 64 * sbuf;
 #pragma unroll
             for (int ks = 0; ks < Cfg::KST; ++ks) {
@@ -233,9 +251,9 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             if (step == T - 1) ptx::umma_commit_mc<CG>(bar(bars.q_empty), 0x3);
             ++g;
           }
-          if (step >= 1) {
-            const uint32_t pbuf = gp & 1;
-            ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp >> 1) & 1);
+          if (step >= LA) {
+            const uint32_t pbuf = gp % KS;
+            ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp / KS) & 1);
             ptx::tc_fence_after();
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
@@ -246,7 +264,7 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               for (int kk = 0; kk < 4; ++kk) {  // 32 keys per MMA: 4 atoms of 8 key-lines
                 const uint64_t ad = ptx::make_smem_desc_sw128(sP + pbuf * 8192 + kk * 32, 16, 1024);
                 const uint64_t bd = ptx::make_smem_desc_sw128(sV + stage * 16384 + kk * 4096, 16384, 1024);
-                ptx::umma_f8_ss<CG>(tmem + 128 * s, ad, bd, idesc_pv, (step > 1 || kk > 0) ? 1u : 0u);
+                ptx::umma_f8_ss<CG>(tmem + 128 * s, ad, bd, idesc_pv, (step > LA || kk > 0) ? 1u : 0u);
               }
               ptx::umma_commit_mc<CG>(bar(bars.v_empty[stage]), 0x3);
               ++vc;
@@ -269,7 +287,6 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const uint32_t rgrp = warp & 1;
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;
     const uint32_t l_p_full0 = ptx::mapa(bar(bars.p_full[0]), 0);
-    const uint32_t l_p_full1 = ptx::mapa(bar(bars.p_full[1]), 0);
     const float NEG_INF = -INFINITY;
     uint32_t g = 0;
     for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
@@ -289,18 +306,20 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       float m = NEG_INF, l = 0.f;
 
       for (int i = 0; i < T; ++i, ++g) {
-        const uint32_t sbuf = g & 1;
+        const uint32_t sbuf = g % KS;
+        const uint32_t xb = g & 1;
         const float mul = qs_c * __ldg(ksp + i);      // dequant * softmax scale * log2(e)
         const float pc = pc_base * __ldg(vsp + i);    // P -> e4m3 range, V scale folded in
-        ptx::mbar_wait(bar(bars.s_full[sbuf]), (g >> 1) & 1);
+        ptx::mbar_wait(bar(bars.s_full[sbuf]), (g / KS) & 1);
         ptx::tc_fence_after();
         uint32_t sr[32];
         ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32 * ch, sr);
         ptx::tmem_wait_ld();
+        // work on the raw MMA output inside the tile (mul > 0 is constant per tile): x = s * mul
         float x[32];
         const int key0 = i * 128 + 64 * (int)kh + 32 * (int)ch;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]) * mul;
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]);
         const bool tail = (i * 128 + 128 > p.seqlen_kv);
         const bool diag = p.causal && (i * 128 + 127 > q0 + (p.seqlen_kv - p.seqlen_q));
         if (tail || diag) {
@@ -316,10 +335,10 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         mx0 = fmax3(mx0, x[20], x[21]); mx1 = fmax3(mx1, x[22], x[23]);
         mx2 = fmax3(mx2, x[24], x[25]); mx3 = fmax3(mx3, x[26], x[27]);
         mx0 = fmax3(mx0, x[28], x[29]); mx1 = fmax3(mx1, x[30], x[31]);
-        float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3);
-        xch[sbuf][slot][row] = tmax;
+        float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3) * mul;   // scaled (log2) domain
+        xch[xb][slot][row] = tmax;
         ptx::named_bar_sync(1 + rgrp, 128);
-        tmax = fmaxf(fmax3(xch[sbuf][0][row], xch[sbuf][1][row], xch[sbuf][2][row]), xch[sbuf][3][row]);
+        tmax = fmaxf(fmax3(xch[xb][0][row], xch[xb][1][row], xch[xb][2][row]), xch[xb][3][row]);
         const float m_new = fmaxf(m, tmax);
         const bool upd = (m_new - m) > kLazyThreshold;
         const float m_use = upd ? m_new : m;
@@ -327,19 +346,28 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const float m_safe = (m_use == NEG_INF) ? 0.f : m_use;
         float factor = 1.f;
         if (need_rescale) factor = exp2f(m - m_use);
+        // P8 = e4m3(exp2(x - m) * pc): fold log2(pc) into the exponent, so the MUFU result is already in the
+        // e4m3 range; the row sum accumulates the scaled values and is unscaled once per tile.
+        const float cadd = (pc > 0.f ? log2f(pc) : 0.f) - m_safe;
+        const float2 mul2 = make_float2(mul, mul), c2 = make_float2(cadd, cadd);
         uint32_t pk[8];
-        float lsum = 0.f;
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float e0 = exp2f(x[j] - m_safe), e1 = exp2f(x[j + 1] - m_safe);
-          const float e2 = exp2f(x[j + 2] - m_safe), e3 = exp2f(x[j + 3] - m_safe);
-          lsum += (e0 + e1) + (e2 + e3);
-          pk[j >> 2] = pack_e4m3x4(e0 * pc, e1 * pc, e2 * pc, e3 * pc);
+          const float2 a0 = ffma2(make_float2(x[j], x[j + 1]), mul2, c2);
+          const float2 a1 = ffma2(make_float2(x[j + 2], x[j + 3]), mul2, c2);
+          const float2 e0 = make_float2(exp2f(a0.x), exp2f(a0.y));
+          const float2 e1 = make_float2(exp2f(a1.x), exp2f(a1.y));
+          acc0 = fadd2(acc0, e0);
+          acc1 = fadd2(acc1, e1);
+          pk[j >> 2] = pack_e4m3x4(e0.x, e0.y, e1.x, e1.y);
         }
+        acc0 = fadd2(acc0, acc1);
+        const float lsum = (acc0.x + acc0.y) * (pc > 0.f ? 1.f / pc : 0.f);
         l = l * factor + lsum;
         m = m_use;
 
-        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((g >> 1) & 1) ^ 1);
+        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((g / KS) & 1) ^ 1);
         {
           // P8 tile: one 128-byte row per query row (128 keys), this thread owns bytes [64kh+32ch, +32)
           const uint32_t prow = sP + sbuf * 8192 + row * 128;
@@ -352,7 +380,7 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
         if (__any_sync(0xffffffffu, need_rescale)) {
-          ptx::mbar_wait(bar(bars.p_empty[(g - 1) & 1]), ((g - 1) >> 1) & 1);
+          ptx::mbar_wait(bar(bars.p_empty[(g - 1) % KS]), ((g - 1) / KS) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
           for (int c0 = (int)ch * (Cfg::O_COLS / 2); c0 < (int)(ch + 1) * (Cfg::O_COLS / 2); c0 += 32) {
@@ -368,13 +396,13 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
-        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(sbuf ? l_p_full1 : l_p_full0);
+        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(l_p_full0 + 8u * sbuf);
       }
 
       // ---------------- epilogue ----------------
       {
         const uint32_t gl = g - 1;
-        ptx::mbar_wait(bar(bars.p_empty[gl & 1]), (gl >> 1) & 1);
+        ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
         ptx::tc_fence_after();
         float (*xl)[64] = xch[gl & 1];
         xl[slot][row] = l;

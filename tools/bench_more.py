@@ -71,7 +71,7 @@ def main():
 
       ms_b = timeit(bwd, 5)
       rec.update({"bwd_ms": ms_b, "bwd_tflops": 2.5 * f / ms_b * 1e-9})
-    if name.startswith("c4"):
+    if name.startswith("c4") or name in ("c2_self_d512", "c2_causal_d512", "d320"):
       be = ffpa_attn.CUDABackend(enable_fp8=True)
       ms8 = timeit(lambda: ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=be, **kw), 10)
       rec.update({"fp8_fwd_ms": ms8, "fp8_fwd_tflops": f / ms8 * 1e-9, "fp8_includes": "quantise pre-pass + attention"})
