@@ -62,12 +62,19 @@ struct FwdCfg {
   static constexpr int MMA_WARP = NSW, TMA_WARP = NSW + 1;
   static constexpr int THREADS = (NSW + 2) * 32;
   static constexpr int P_BYTES = KSTG * 16384;
-  static constexpr int NVS = HD > 768 ? 1 : 2;  // 32 KB V stages
+  // Wide heads keep Q resident (96-128 KB), leaving too little for separate K and V rings; they use
+  // ONE ring of 16 KB stages shared by K stages and V slices (a slice = 2 consecutive stages), so
+  // loads can run a full ring ahead regardless of operand. Needs even stage counts per tile.
+  static constexpr bool UNIFIED = HD > 512 && (KST % 2 == 0) && (DVP % 256 == 0);
+  static constexpr int NVS = HD > 768 ? 1 : 2;           // 32 KB V stages (separate-ring mode)
+  static constexpr int NVS_ALLOC = UNIFIED ? 0 : NVS;
   static constexpr int kBudget = kSmemLimit - (NSW == 16 ? 5120 : 3072);  // static smem (barriers + exchange), 1 KB aligned
-  static constexpr int kNksRaw = (kBudget - Q_BYTES - P_BYTES - NVS * 32768) / 16384;
-  static constexpr int NKS = kNksRaw > 8 ? 8 : kNksRaw;   // 16 KB K stages
-  static constexpr int SMEM_DYN = Q_BYTES + P_BYTES + NKS * 16384 + NVS * 32768;
+  static constexpr int kNksRaw = (kBudget - Q_BYTES - P_BYTES - NVS_ALLOC * 32768) / 16384;
+  static constexpr int kNksCap = kNksRaw > 8 ? 8 : kNksRaw;
+  static constexpr int NKS = UNIFIED ? (kNksCap & ~1) : kNksCap;   // 16 KB K stages (or unified ring stages)
+  static constexpr int SMEM_DYN = Q_BYTES + P_BYTES + NKS * 16384 + NVS_ALLOC * 32768;
   static_assert(NKS >= 2, "not enough shared memory for the K ring");
+  static_assert(!UNIFIED || (NKS % 2 == 0 && NKS >= 4), "unified ring needs an even number of stages");
   static_assert(S_BASE + 64 * KSTG <= 512 && S_BASE >= O_COLS, "O does not fit TMEM next to S");
   // width of the O slab of pass `pass`, and N of its slice s
   __host__ __device__ static constexpr int slab_w(int pass) { return (DVP - pass * DSLAB) >= DSLAB ? DSLAB : (DVP - pass * DSLAB); }
@@ -238,6 +245,18 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
               if (256 * s >= dvw) break;
+              if constexpr (Cfg::UNIFIED) {
+                // slice = stages (st, st+1) of the shared ring; kc is the shared counter
+                const uint32_t st = kc % Cfg::NKS, n = kc / Cfg::NKS;
+                for (int bx = 0; bx < 2; ++bx) {
+                  ptx::mbar_wait(bar(bars.k_empty[st + bx]), (n & 1) ^ 1);
+                  if (rank == 0) ptx::mbar_expect_tx(bar(bars.k_full[st + bx]), 2 * 16384);
+                  ptx::tma_load_4d_2sm(sK + (st + bx) * 16384, &map_v, ptx::mapa(bar(bars.k_full[st + bx]), 0),
+                                       dv0 + 256 * s + 128 * (int)rank + 64 * bx, kv0, hk, b);
+                }
+                kc += 2;
+                continue;
+              }
               const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
               ptx::mbar_wait(bar(bars.v_empty[stage]), (n & 1) ^ 1);
               const int ns = Cfg::slice_n(dvw, s);
@@ -302,6 +321,23 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
               if (256 * s >= dvw) break;
+              if constexpr (Cfg::UNIFIED) {
+                const uint32_t st = kc % Cfg::NKS, n = kc / Cfg::NKS;
+                ptx::mbar_wait(bar(bars.k_full[st]), n & 1);
+                ptx::mbar_wait(bar(bars.k_full[st + 1]), n & 1);
+                ptx::tc_fence_after();
+                const uint32_t idesc_pv = ptx::make_idesc(fmt, fmt, 0, 1, 128, 256);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                  const uint64_t ad = ptx::make_smem_desc_sw128(sP + pbuf * 16384 + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
+                  const uint64_t bd = ptx::make_smem_desc_sw128(sK + st * 16384 + kk * 2048, 16384, 1024);
+                  ptx::umma_f16_ss<CG>(tmem + 128 * s, ad, bd, idesc_pv, (step > LA || kk > 0) ? 1u : 0u);
+                }
+                ptx::umma_commit_mc<CG>(bar(bars.k_empty[st]), 0x3);
+                ptx::umma_commit_mc<CG>(bar(bars.k_empty[st + 1]), 0x3);
+                kc += 2;
+                continue;
+              }
               const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
               ptx::mbar_wait(bar(bars.v_full[stage]), n & 1);
               ptx::tc_fence_after();
