@@ -23,6 +23,10 @@
 #include "ffpa_internal.h"
 #include "sm100_ptx.cuh"
 
+#ifndef FFPA_UNIFIED_MIN_HD
+#define FFPA_UNIFIED_MIN_HD 512
+#endif
+
 namespace ffpa {
 
 constexpr int kSmemLimit = 232448;
@@ -65,7 +69,8 @@ struct FwdCfg {
   // Wide heads keep Q resident (96-128 KB), leaving too little for separate K and V rings; they use
   // ONE ring of 16 KB stages shared by K stages and V slices (a slice = 2 consecutive stages), so
   // loads can run a full ring ahead regardless of operand. Needs even stage counts per tile.
-  static constexpr bool UNIFIED = HD > 512 && (KST % 2 == 0) && (DVP % 256 == 0);
+  static constexpr bool UNIFIED = HD > FFPA_UNIFIED_MIN_HD;
+  static constexpr bool K_DUMMY = UNIFIED && (KST % 2 == 1);   // pad the K stages of a tile to an even count
   static constexpr int NVS = HD > 768 ? 1 : 2;           // 32 KB V stages (separate-ring mode)
   static constexpr int NVS_ALLOC = UNIFIED ? 0 : NVS;
   static constexpr int kBudget = kSmemLimit - (NSW == 16 ? 5120 : 3072);  // static smem (barriers + exchange), 1 KB aligned
@@ -239,6 +244,12 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                      kv0 + 64 * (int)rank, hk, b);
               ++kc;
             }
+            if constexpr (Cfg::K_DUMMY) {  // keep V slices on even ring stages
+              const uint32_t st = kc % Cfg::NKS, n = kc / Cfg::NKS;
+              ptx::mbar_wait(bar(bars.k_empty[st]), (n & 1) ^ 1);
+              if (rank == 0) ptx::mbar_arrive(bar(bars.k_full[st]));
+              ++kc;
+            }
           }
           if (step >= LA) {
             const int kv0 = (step - LA) * 128;
@@ -248,11 +259,16 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               if constexpr (Cfg::UNIFIED) {
                 // slice = stages (st, st+1) of the shared ring; kc is the shared counter
                 const uint32_t st = kc % Cfg::NKS, n = kc / Cfg::NKS;
+                const int nsu = Cfg::slice_n(dvw, s);
                 for (int bx = 0; bx < 2; ++bx) {
                   ptx::mbar_wait(bar(bars.k_empty[st + bx]), (n & 1) ^ 1);
-                  if (rank == 0) ptx::mbar_expect_tx(bar(bars.k_full[st + bx]), 2 * 16384);
-                  ptx::tma_load_4d_2sm(sK + (st + bx) * 16384, &map_v, ptx::mapa(bar(bars.k_full[st + bx]), 0),
-                                       dv0 + 256 * s + 128 * (int)rank + 64 * bx, kv0, hk, b);
+                  if (bx < nsu / 128) {
+                    if (rank == 0) ptx::mbar_expect_tx(bar(bars.k_full[st + bx]), 2 * 16384);
+                    ptx::tma_load_4d_2sm(sK + (st + bx) * 16384, &map_v, ptx::mapa(bar(bars.k_full[st + bx]), 0),
+                                         dv0 + 256 * s + (nsu / 2) * (int)rank + 64 * bx, kv0, hk, b);
+                  } else if (rank == 0) {
+                    ptx::mbar_arrive(bar(bars.k_full[st + bx]));  // unused half of a 128-wide slice
+                  }
                 }
                 kc += 2;
                 continue;
@@ -310,6 +326,12 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               ptx::umma_commit_mc<CG>(bar(bars.k_empty[stage]), 0x3);
               ++kc;
             }
+            if constexpr (Cfg::K_DUMMY) {
+              const uint32_t st = kc % Cfg::NKS, n = kc / Cfg::NKS;
+              ptx::mbar_wait(bar(bars.k_full[st]), n & 1);
+              ptx::umma_commit_mc<CG>(bar(bars.k_empty[st]), 0x3);
+              ++kc;
+            }
             ptx::umma_commit_mc<CG>(bar(bars.s_full[sbuf]), 0x3);
             if (step == T - 1) ptx::umma_commit_mc<CG>(bar(bars.q_empty), 0x3);
             ++g;
@@ -326,7 +348,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 ptx::mbar_wait(bar(bars.k_full[st]), n & 1);
                 ptx::mbar_wait(bar(bars.k_full[st + 1]), n & 1);
                 ptx::tc_fence_after();
-                const uint32_t idesc_pv = ptx::make_idesc(fmt, fmt, 0, 1, 128, 256);
+                const uint32_t idesc_pv = ptx::make_idesc(fmt, fmt, 0, 1, 128, Cfg::slice_n(dvw, s));
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                   const uint64_t ad = ptx::make_smem_desc_sw128(sP + pbuf * 16384 + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
