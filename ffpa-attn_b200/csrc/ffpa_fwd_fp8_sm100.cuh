@@ -55,9 +55,9 @@ struct Fp8Cfg {
   static constexpr int KST = (NB + 1) / 2;         // 16 KB K stages ([64 keys x 256 d]) per KV tile
   static constexpr int S_BASE = 256;
   static constexpr int Q_BYTES = NB * 8192;
-  static constexpr int KSTG = HD <= 256 ? 4 : 2;   // S (TMEM) / P (SMEM) pipeline depth
+  static constexpr int KSTG = 4;   // S (TMEM) / P (SMEM) pipeline depth (O_COLS <= 256 leaves 4 x 64 columns)
   static constexpr int P_BYTES = KSTG * 8192;
-  static constexpr int kBudget = kSmemLimit - 3072;
+  static constexpr int kBudget = kSmemLimit - 5120;   // static smem: barriers, exchange buffers
   static constexpr int kAvail = (kBudget - Q_BYTES - P_BYTES) / 16384;
   static constexpr int NVS = (kAvail / 2) > 6 ? 6 : (kAvail / 2);    // 16 KB V stages ([128 keys x 128 d])
   static constexpr int NKS = (kAvail - NVS) > 8 ? 8 : (kAvail - NVS);
@@ -72,6 +72,7 @@ struct Barriers {
   uint64_t v_full[6], v_empty[6];
   uint64_t s_full[4];
   uint64_t p_full[4], p_empty[4];
+  uint64_t m_full[4];
 };
 
 __device__ __forceinline__ int num_kv_tiles(const Fp8KernelParams& p, int q0) {
@@ -123,7 +124,10 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   constexpr int LA = Cfg::KSTG - 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ Barriers bars;
-  __shared__ float xch[2][4][64];
+  __shared__ float xchw[2][2][2][64];  // row-max exchange between the two lane halves: [wg][parity][kh][row]
+  __shared__ float mval[4][64];        // running row max, published per tile (ring of 4: a lagging warp of the
+                                       // consumer warpgroup is at most one of its own tiles behind)
+  __shared__ float xl[4][64];          // end-of-item row-sum exchange
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
@@ -146,9 +150,10 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     for (int i = 0; i < 6; ++i) { ptx::mbar_init(bar(bars.v_full[i]), 1); ptx::mbar_init(bar(bars.v_empty[i]), 1); }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(bar(bars.s_full[i]), 1);
-      ptx::mbar_init(bar(bars.p_full[i]), 2 * kSoftmaxWarps);
+      ptx::mbar_init(bar(bars.p_full[i]), kSoftmaxWarps);  // 4 warps of one warpgroup x 2 CTAs
       ptx::mbar_init(bar(bars.p_empty[i]), 1);
     }
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(bar(bars.m_full[i]), 2);  // the two kh == 0 warps of the publishing warpgroup
     ptx::fence_mbar_init();
   }
   if (warp == kTmaWarp && ptx::elect_one()) {
@@ -278,17 +283,24 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncwarp();
   } else {
     // =========================================== softmax / correction / epilogue ================
+    // Two warpgroups work on ALTERNATE KV tiles (wg = tile parity), each thread owning one TMEM lane
+    // (row, 64-key half) of its tile. Tiles i and i+1 are therefore in different phases of
+    // load / max / exp2 / pack, so the MUFU pipe of one overlaps the ALU work of the other (with
+    // column-split warpgroups both sit in the same phase of the same tile, see
+    // profiles/r01_fwd_small_d_ncu.md). The only cross-warpgroup dependency is the running row max,
+    // published through SMEM + an mbarrier right after a tile's max is known.
     const uint32_t t = threadIdx.x;
+    const uint32_t wg = t >> 7;               // tile parity handled by this warpgroup
     const uint32_t lane128 = t & 127;
     const uint32_t row = lane128 & 63;
-    const uint32_t kh = lane128 >> 6;
-    const uint32_t ch = t >> 7;
-    const uint32_t slot = kh * 2 + ch;
-    const uint32_t rgrp = warp & 1;
+    const uint32_t kh = lane128 >> 6;         // 64-key half of the KV tile / column half of O
+    const uint32_t rgrp = warp & 1;           // rows 0-31 / 32-63
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;
     const uint32_t l_p_full0 = ptx::mapa(bar(bars.p_full[0]), 0);
     const float NEG_INF = -INFINITY;
-    uint32_t g = 0;
+    uint32_t g = 0;                           // global tile counter at the start of the item
+    uint32_t pub[4] = {0, 0, 0, 0};           // completed publications of m_full[0..3]
+    uint32_t uw = 0;                          // tiles processed by this warpgroup (exchange buffer parity)
     for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
       const int mt = item % p.n_mtiles;
       const int bh = item / p.n_mtiles;
@@ -303,57 +315,69 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const float* vsp = p.vs + ((int64_t)b * p.heads_kv + hk) * p.tk;
       const float vref = p.vref[(int64_t)b * p.heads_kv + hk];
       const float pc_base = vref > 0.f ? kPScale / vref : 0.f;
-      float m = NEG_INF, l = 0.f;
+      float m_l = NEG_INF, l = 0.f;           // partial row sum of this thread, relative to m_l
 
-      for (int i = 0; i < T; ++i, ++g) {
-        const uint32_t sbuf = g % KS;
-        const uint32_t xb = g & 1;
-        const float mul = qs_c * __ldg(ksp + i);      // dequant * softmax scale * log2(e)
-        const float pc = pc_base * __ldg(vsp + i);    // P -> e4m3 range, V scale folded in
-        ptx::mbar_wait(bar(bars.s_full[sbuf]), (g / KS) & 1);
+      for (int i = (int)wg; i < T; i += 2, ++uw) {
+        const uint32_t gi = g + (uint32_t)i;
+        const uint32_t sbuf = gi % KS;
+        const uint32_t xb = uw & 1;
+        const float mul = qs_c * __ldg(ksp + i);
+        const float pc = pc_base * __ldg(vsp + i);
+        ptx::mbar_wait(bar(bars.s_full[sbuf]), (gi / KS) & 1);
         ptx::tc_fence_after();
-        uint32_t sr[32];
-        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32 * ch, sr);
+        uint32_t sr[64];
+        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf, sr);
+        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32, sr + 32);
         ptx::tmem_wait_ld();
-        // work on the raw MMA output inside the tile (mul > 0 is constant per tile): x = s * mul
-        float x[32];
-        const int key0 = i * 128 + 64 * (int)kh + 32 * (int)ch;
+        float x[64];
+        const int key0 = i * 128 + 64 * (int)kh;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]);
+        for (int j = 0; j < 64; ++j) x[j] = __uint_as_float(sr[j]);
         const bool tail = (i * 128 + 128 > p.seqlen_kv);
         const bool diag = p.causal && (i * 128 + 127 > q0 + (p.seqlen_kv - p.seqlen_q));
         if (tail || diag) {
           const int lim = p.causal ? (causal_lim < p.seqlen_kv - 1 ? causal_lim : p.seqlen_kv - 1) : p.seqlen_kv - 1;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < 64; ++j)
             if (key0 + j > lim) x[j] = NEG_INF;
         }
         float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
         float mx2 = fmax3(x[6], x[7], x[8]), mx3 = fmax3(x[9], x[10], x[11]);
-        mx0 = fmax3(mx0, x[12], x[13]); mx1 = fmax3(mx1, x[14], x[15]);
-        mx2 = fmax3(mx2, x[16], x[17]); mx3 = fmax3(mx3, x[18], x[19]);
-        mx0 = fmax3(mx0, x[20], x[21]); mx1 = fmax3(mx1, x[22], x[23]);
-        mx2 = fmax3(mx2, x[24], x[25]); mx3 = fmax3(mx3, x[26], x[27]);
-        mx0 = fmax3(mx0, x[28], x[29]); mx1 = fmax3(mx1, x[30], x[31]);
+#pragma unroll
+        for (int j = 12; j < 60; j += 12) {
+          mx0 = fmax3(mx0, x[j], x[j + 1]); mx1 = fmax3(mx1, x[j + 2], x[j + 3]);
+          mx2 = fmax3(mx2, x[j + 4], x[j + 5]); mx3 = fmax3(mx3, x[j + 6], x[j + 7]);
+          mx0 = fmax3(mx0, x[j + 8], x[j + 9]); mx1 = fmax3(mx1, x[j + 10], x[j + 11]);
+        }
+        mx2 = fmax3(mx2, x[60], x[61]); mx3 = fmax3(mx3, x[62], x[63]);
         float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3) * mul;   // scaled (log2) domain
-        xch[xb][slot][row] = tmax;
-        ptx::named_bar_sync(1 + rgrp, 128);
-        tmax = fmaxf(fmax3(xch[xb][0][row], xch[xb][1][row], xch[xb][2][row]), xch[xb][3][row]);
-        const float m_new = fmaxf(m, tmax);
-        const bool upd = (m_new - m) > kLazyThreshold;
-        const float m_use = upd ? m_new : m;
-        const bool need_rescale = upd && (m != NEG_INF);
+        xchw[wg][xb][kh][row] = tmax;
+        ptx::named_bar_sync(1 + 2 * wg + rgrp, 64);
+        tmax = fmaxf(tmax, xchw[wg][xb][kh ^ 1][row]);
+        // running max of tile i-1, published by the other warpgroup
+        float m_prev = NEG_INF;
+        if (i > 0) {
+          const uint32_t par = (uint32_t)(i - 1) & 3u;
+          const uint32_t cnt = pub[par] + (uint32_t)((i - 1) >> 2);
+          ptx::mbar_wait(bar(bars.m_full[par]), cnt & 1);
+          m_prev = mval[par][row];
+        }
+        const float m_new = fmaxf(m_prev, tmax);
+        const bool upd = (m_new - m_prev) > kLazyThreshold;
+        const float m_use = upd ? m_new : m_prev;
+        const bool need_rescale = upd && (m_prev != NEG_INF);
+        if (kh == 0) mval[i & 3][row] = m_use;
+        __syncwarp();
+        if (kh == 0 && ptx::lane_id() == 0) ptx::mbar_arrive(bar(bars.m_full[i & 3]));
         const float m_safe = (m_use == NEG_INF) ? 0.f : m_use;
         float factor = 1.f;
-        if (need_rescale) factor = exp2f(m - m_use);
-        // P8 = e4m3(exp2(x - m) * pc): fold log2(pc) into the exponent, so the MUFU result is already in the
-        // e4m3 range; the row sum accumulates the scaled values and is unscaled once per tile.
+        if (need_rescale) factor = exp2f(m_prev - m_use);
         const float cadd = (pc > 0.f ? log2f(pc) : 0.f) - m_safe;
         const float2 mul2 = make_float2(mul, mul), c2 = make_float2(cadd, cadd);
-        uint32_t pk[8];
+        uint32_t pk[16];
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 64; j += 4) {
           const float2 a0 = ffma2(make_float2(x[j], x[j + 1]), mul2, c2);
           const float2 a1 = ffma2(make_float2(x[j + 2], x[j + 3]), mul2, c2);
           const float2 e0 = make_float2(exp2f(a0.x), exp2f(a0.y));
@@ -364,26 +388,29 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         acc0 = fadd2(acc0, acc1);
         const float lsum = (acc0.x + acc0.y) * (pc > 0.f ? 1.f / pc : 0.f);
-        l = l * factor + lsum;
-        m = m_use;
+        // partial row sum, re-expressed relative to the max in effect
+        if (m_l != m_use) l *= (m_l == NEG_INF) ? 0.f : exp2f(m_l - m_use);
+        l += lsum;
+        m_l = m_use;
 
-        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((g / KS) & 1) ^ 1);
+        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((gi / KS) & 1) ^ 1);
         {
-          // P8 tile: one 128-byte row per query row (128 keys), this thread owns bytes [64kh+32ch, +32)
+          // P8 tile: one 128-byte row per query row; this thread owns bytes [64 kh, 64 kh + 64)
           const uint32_t prow = sP + sbuf * 8192 + row * 128;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t addr = prow + (((4 * kh + 2 * ch + c) ^ (row & 7)) << 4);
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = prow + (((4 * kh + c) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
                          "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
                          : "memory");
           }
         }
         if (__any_sync(0xffffffffu, need_rescale)) {
-          ptx::mbar_wait(bar(bars.p_empty[(g - 1) % KS]), ((g - 1) / KS) & 1);
+          // O may only be touched once PV of tile i-1 has retired; this warpgroup scales all columns
+          ptx::mbar_wait(bar(bars.p_empty[(gi - 1) % KS]), ((gi - 1) / KS) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int c0 = (int)ch * (Cfg::O_COLS / 2); c0 < (int)(ch + 1) * (Cfg::O_COLS / 2); c0 += 32) {
+          for (int c0 = 0; c0 < Cfg::O_COLS; c0 += 32) {
             uint32_t orr[32];
             ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
             ptx::tmem_wait_ld();
@@ -401,13 +428,20 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
       // ---------------- epilogue ----------------
       {
-        const uint32_t gl = g - 1;
+        // final running max: published with the last tile
+        const uint32_t parl = (uint32_t)(T - 1) & 3u;
+        const uint32_t cntl = pub[parl] + (uint32_t)((T - 1) >> 2);
+        ptx::mbar_wait(bar(bars.m_full[parl]), cntl & 1);
+        const float m_fin = mval[parl][row];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pub[j] += (T > j) ? (uint32_t)((T - 1 - j) / 4 + 1) : 0u;
+        const float l_fin = (m_l == NEG_INF) ? 0.f : l * exp2f(m_l - m_fin);
+        xl[wg * 2 + kh][row] = l_fin;
+        ptx::named_bar_sync(5 + rgrp, 128);   // both warpgroups: nobody enters the next item before m_fin is read
+        const float l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
+        const uint32_t gl = g + (uint32_t)T - 1;
         ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
         ptx::tc_fence_after();
-        float (*xl)[64] = xch[gl & 1];
-        xl[slot][row] = l;
-        ptx::named_bar_sync(1 + rgrp, 128);
-        const float l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
         const float inv = l_tot > 0.f ? (vref / kPScale) / l_tot : 0.f;
         const bool row_ok = gq < p.seqlen_q;
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
@@ -415,7 +449,7 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
         for (int s = 0; s < Cfg::NSLICE; ++s) {
 #pragma unroll 1
-          for (int c0 = (int)ch * 64; c0 < (int)(ch + 1) * 64; c0 += 32) {
+          for (int c0 = (int)wg * 64; c0 < (int)(wg + 1) * 64; c0 += 32) {
             uint32_t orr[32];
             ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
             ptx::tmem_wait_ld();
@@ -438,11 +472,14 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
           }
         }
-        if (p.lse != nullptr && slot == 0 && row_ok) {
-          const float lse = (l_tot > 0.f) ? (m + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
+        if (p.lse != nullptr && wg == 0 && kh == 0 && row_ok) {
+          const float lse = (l_tot > 0.f) ? (m_fin + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
           p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
         }
         ptx::tc_fence_before();
+        // xl is reused by the next item: all four writers must be past their reads first
+        ptx::named_bar_sync(5 + rgrp, 128);
+        g += (uint32_t)T;
       }
     }
   }
