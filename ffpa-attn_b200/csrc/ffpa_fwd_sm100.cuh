@@ -23,6 +23,9 @@
 #include "ffpa_internal.h"
 #include "sm100_ptx.cuh"
 
+#ifndef FFPA_ALT_MAX_HD
+#define FFPA_ALT_MAX_HD 256
+#endif
 #ifndef FFPA_UNIFIED_MIN_HD
 #define FFPA_UNIFIED_MIN_HD 512
 #endif
@@ -61,8 +64,13 @@ struct FwdCfg {
   // limit there is pipe throughput (MUFU.EX2 + conversions), not latency hiding -- so 8 is used everywhere;
   // the kernel stays generic in NSW.
   static constexpr int NSW = 8;
-  static constexpr int CQ = NSW / 4;        // column groups of the 64-column S stage
-  static constexpr int CPT = 64 / CQ;       // S columns (keys) per thread and tile
+  // ALT: the two softmax warpgroups take ALTERNATE KV tiles (each thread a whole 64-key lane of its
+  // tile) instead of splitting the columns of one tile; tiles i and i+1 are then in different phases
+  // (load / max / exp2 / pack) so MUFU and ALU work overlap. Pays off when the SIMT side is the limiter
+  // (small heads; the FP8 kernel always uses it). Needs NSW == 8.
+  static constexpr bool ALT = HD <= FFPA_ALT_MAX_HD;
+  static constexpr int CQ = ALT ? 1 : NSW / 4;   // column groups of the 64-column S stage
+  static constexpr int CPT = 64 / CQ;            // S columns (keys) per thread and tile
   static constexpr int MMA_WARP = NSW, TMA_WARP = NSW + 1;
   static constexpr int THREADS = (NSW + 2) * 32;
   static constexpr int P_BYTES = KSTG * 16384;
@@ -73,7 +81,7 @@ struct FwdCfg {
   static constexpr bool K_DUMMY = UNIFIED && (KST % 2 == 1);   // pad the K stages of a tile to an even count
   static constexpr int NVS = HD > 768 ? 1 : 2;           // 32 KB V stages (separate-ring mode)
   static constexpr int NVS_ALLOC = UNIFIED ? 0 : NVS;
-  static constexpr int kBudget = kSmemLimit - (NSW == 16 ? 5120 : 3072);  // static smem (barriers + exchange), 1 KB aligned
+  static constexpr int kBudget = kSmemLimit - ((NSW == 16 || ALT) ? 5120 : 3072);  // static smem (barriers + exchange), 1 KB aligned
   static constexpr int kNksRaw = (kBudget - Q_BYTES - P_BYTES - NVS_ALLOC * 32768) / 16384;
   static constexpr int kNksCap = kNksRaw > 8 ? 8 : kNksRaw;
   static constexpr int NKS = UNIFIED ? (kNksCap & ~1) : kNksCap;   // 16 KB K stages (or unified ring stages)
@@ -92,6 +100,7 @@ struct Barriers {
   uint64_t v_full[3], v_empty[3];
   uint64_t s_full[4];
   uint64_t p_full[4], p_empty[4];
+  uint64_t m_full[4];
 };
 
 __device__ __forceinline__ int num_kv_tiles(const FwdKernelParams& p, int q0) {
@@ -162,7 +171,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   __shared__ Barriers bars;
   constexpr int kMmaWarp = Cfg::MMA_WARP, kTmaWarp = Cfg::TMA_WARP, kSoftmaxWarps = Cfg::NSW;
   constexpr int CQ = Cfg::CQ, CPT = Cfg::CPT;
-  __shared__ float xch[2][2 * Cfg::CQ][64];  // per-tile row-max exchange: [parity][kh*CQ+ch][row]
+  __shared__ float xch[2][Cfg::ALT ? 4 : 2 * Cfg::CQ][64];  // row-max exchange: [parity][kh*CQ+ch][row]  (ALT: [parity][wg*2+kh][row])
+  __shared__ float mval[Cfg::ALT ? 4 : 1][64];             // ALT: running row max published per tile (ring of 4)
+  constexpr bool ALT = Cfg::ALT;
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
@@ -186,7 +197,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     for (int i = 0; i < 3; ++i) { ptx::mbar_init(bar(bars.v_full[i]), 1); ptx::mbar_init(bar(bars.v_empty[i]), 1); }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(bar(bars.s_full[i]), 1);
-      ptx::mbar_init(bar(bars.p_full[i]), 2 * kSoftmaxWarps);  // softmax warps of both CTAs
+      ptx::mbar_init(bar(bars.p_full[i]), Cfg::ALT ? kSoftmaxWarps : 2 * kSoftmaxWarps);  // softmax warps (of one tile) of both CTAs
+      ptx::mbar_init(bar(bars.m_full[i]), 2);
       ptx::mbar_init(bar(bars.p_empty[i]), 1);
     }
     ptx::fence_mbar_init();
@@ -388,15 +400,18 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t lane128 = t & 127;
     const uint32_t row = lane128 & 63;        // row inside this CTA's 64
     const uint32_t kh = lane128 >> 6;         // 64-key half of the KV tile / column half of O
-    const uint32_t ch = t >> 7;               // column half inside the S stage
-    const uint32_t slot = kh * CQ + ch;
+    const uint32_t wgi = t >> 7;              // warpgroup index
+    const uint32_t ch = ALT ? 0u : wgi;       // column group inside the S stage (column-split mode)
+    const uint32_t slot = ALT ? (wgi * 2 + kh) : (kh * CQ + ch);
     const uint32_t rgrp = warp & 1;           // warps sharing rows: {0,2,4,6} / {1,3,5,7}
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;
     const uint32_t l_p_full0 = ptx::mapa(bar(bars.p_full[0]), 0);
     const float NEG_INF = -INFINITY;
     // softmax domain: fast mode works on raw scores (mul = scale*log2e), general on scaled+biased
     const float mul = (MODE == kModeFast) ? p.scale_log2 : 1.0f;
-    uint32_t g = 0;
+    uint32_t g = 0;                      // global tile counter at the start of the item (ALT) / running (column split)
+    uint32_t uw = 0;                     // ALT: tiles processed by this warpgroup
+    uint32_t pub[4] = {0, 0, 0, 0};      // ALT: completed publications of m_full[0..3]
     for (uint32_t kidx = 0;; ++kidx) {
       const int item_s = next_item(p, cluster, nclusters, kidx);
       if (item_s < 0) break;
@@ -410,15 +425,19 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int dv0 = pass * Cfg::DSLAB, dvw = Cfg::slab_w(pass);
       const int gq = q0 + 64 * (int)rank + (int)row;  // global query row of this thread
       const int causal_lim = gq + (p.seqlen_kv - p.seqlen_q);  // last visible key when causal
-      float m = NEG_INF, l = 0.f;
+      float m = NEG_INF, l = 0.f;   // ALT: m = the max this thread's partial sum l is expressed against
 
-      for (int i = 0; i < T; ++i, ++g) {
-        const uint32_t sbuf = g % KS;   // S / P pipeline stage
-        const uint32_t xb = g & 1;      // row-max exchange buffer
-        ptx::mbar_wait(bar(bars.s_full[sbuf]), (g / KS) & 1);
+      for (int i = ALT ? (int)wgi : 0; i < T; i += ALT ? 2 : 1) {
+        const uint32_t gi = ALT ? g + (uint32_t)i : g;   // global index of this tile
+        const uint32_t sbuf = gi % KS;   // S / P pipeline stage
+        const uint32_t xb = ALT ? (uw & 1) : (gi & 1);   // row-max exchange buffer
+        ptx::mbar_wait(bar(bars.s_full[sbuf]), (gi / KS) & 1);
         ptx::tc_fence_after();
         uint32_t sr[CPT];
-        if constexpr (CPT == 32) ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + CPT * ch, sr);
+        if constexpr (CPT == 64) {
+          ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf, sr);
+          ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32, sr + 32);
+        } else if constexpr (CPT == 32) ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + CPT * ch, sr);
         else ptx::tmem_ld_x16(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + CPT * ch, sr);
         ptx::tmem_wait_ld();
         float x[CPT];
@@ -458,28 +477,53 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
         float mx2 = fmax3(x[6], x[7], x[8]), mx3 = fmax3(x[9], x[10], x[11]);
         mx0 = fmax3(mx0, x[12], x[13]); mx1 = fmax3(mx1, x[14], x[15]);
-        if constexpr (CPT == 32) {
+        if constexpr (CPT >= 32) {
           mx2 = fmax3(mx2, x[16], x[17]); mx3 = fmax3(mx3, x[18], x[19]);
           mx0 = fmax3(mx0, x[20], x[21]); mx1 = fmax3(mx1, x[22], x[23]);
           mx2 = fmax3(mx2, x[24], x[25]); mx3 = fmax3(mx3, x[26], x[27]);
           mx0 = fmax3(mx0, x[28], x[29]); mx1 = fmax3(mx1, x[30], x[31]);
         }
+        if constexpr (CPT == 64) {
+#pragma unroll
+          for (int j = 32; j < 64; j += 8) {
+            mx0 = fmax3(mx0, x[j], x[j + 1]); mx1 = fmax3(mx1, x[j + 2], x[j + 3]);
+            mx2 = fmax3(mx2, x[j + 4], x[j + 5]); mx3 = fmax3(mx3, x[j + 6], x[j + 7]);
+          }
+        }
         float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3);
         xch[xb][slot][row] = tmax;
-        ptx::named_bar_sync(1 + rgrp, kSoftmaxWarps * 16);
-        tmax = fmaxf(fmax3(xch[xb][0][row], xch[xb][1][row], xch[xb][2][row]), xch[xb][3][row]);
-        if constexpr (CQ == 4)
-          tmax = fmaxf(tmax, fmaxf(fmax3(xch[xb][4][row], xch[xb][5][row], xch[xb][6][row]), xch[xb][7][row]));
+        if constexpr (ALT) {
+          ptx::named_bar_sync(1 + 2 * wgi + rgrp, 64);      // the two lane halves of this warpgroup's rows
+          tmax = fmaxf(tmax, xch[xb][slot ^ 1][row]);
+          // running max after tile i-1, published by the other warpgroup
+          if (i > 0) {
+            const uint32_t par = (uint32_t)(i - 1) & 3u;
+            const uint32_t cnt = pub[par] + (uint32_t)((i - 1) >> 2);
+            ptx::mbar_wait(bar(bars.m_full[par]), cnt & 1);
+          }
+        } else {
+          ptx::named_bar_sync(1 + rgrp, kSoftmaxWarps * 16);
+          tmax = fmaxf(fmax3(xch[xb][0][row], xch[xb][1][row], xch[xb][2][row]), xch[xb][3][row]);
+          if constexpr (CQ == 4)
+            tmax = fmaxf(tmax, fmaxf(fmax3(xch[xb][4][row], xch[xb][5][row], xch[xb][6][row]), xch[xb][7][row]));
+        }
+        // ALT: m_run = running max after the previous tile (from the other warpgroup); else the local state
+        const float m_run = ALT ? ((i > 0) ? mval[(i - 1) & 3][row] : NEG_INF) : m;
         // lazy rescale: keep the stale max while the true max is < 8 (log2 units) above it
         // (/root/reference/csrc/cuffpa/native/prefill.cuh:719-738, common.cuh:14-18)
-        const float m_new = fmaxf(m, tmax);
-        const bool upd = (m_new - m) * mul > 8.0f;  // true for -inf -> finite; false for -inf -> -inf
-        const float m_use = upd ? m_new : m;
-        const bool need_rescale = upd && (m != NEG_INF);
+        const float m_new = fmaxf(m_run, tmax);
+        const bool upd = (m_new - m_run) * mul > 8.0f;  // true for -inf -> finite; false for -inf -> -inf
+        const float m_use = upd ? m_new : m_run;
+        const bool need_rescale = upd && (m_run != NEG_INF);
+        if constexpr (ALT) {
+          if (kh == 0) mval[i & 3][row] = m_use;
+          __syncwarp();
+          if (kh == 0 && ptx::lane_id() == 0) ptx::mbar_arrive(bar(bars.m_full[i & 3]));
+        }
         const float m_safe = (m_use == NEG_INF) ? 0.f : m_use;
         const float neg_mc = -m_safe * mul;
         float factor = 1.f;
-        if (need_rescale) factor = exp2f((m - m_use) * mul);
+        if (need_rescale) factor = exp2f((m_run - m_use) * mul);
         uint32_t pk[CPT / 2];
         float lsum;
         if constexpr (MODE == kModeDropout) {
@@ -523,11 +567,17 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           acc0 = fadd2(acc0, acc1);
           lsum = acc0.x + acc0.y;
         }
-        l = l * factor + lsum;
+        if constexpr (ALT) {
+          // this thread's partial row sum, re-expressed against the max now in effect
+          if (m != m_use) l *= (m == NEG_INF) ? 0.f : exp2f((m - m_use) * mul);
+          l += lsum;
+        } else {
+          l = l * factor + lsum;
+        }
         m = m_use;
 
         // P buffer free? (PV of tile g-2 retired)
-        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((g / KS) & 1) ^ 1);
+        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((gi / KS) & 1) ^ 1);
         {
           const uint32_t prow = sP + sbuf * 16384 + kh * 8192 + row * 128;
 #pragma unroll
@@ -540,17 +590,18 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         if (__any_sync(0xffffffffu, need_rescale)) {
           // O may only be touched once PV of tile g-1 has retired; each warpgroup scales half the columns
-          ptx::mbar_wait(bar(bars.p_empty[(g - 1) % KS]), ((g - 1) / KS) & 1);
+          ptx::mbar_wait(bar(bars.p_empty[(gi - 1) % KS]), ((gi - 1) / KS) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int c0 = (int)ch * (dvw / 2 / CQ); c0 < (int)(ch + 1) * (dvw / 2 / CQ); c0 += CPT) {
-            uint32_t orr[CPT];
-            if constexpr (CPT == 32) ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
+          constexpr int RC = CPT == 16 ? 16 : 32;   // columns per TMEM round trip
+          for (int c0 = (int)ch * (dvw / 2 / CQ); c0 < (int)(ch + 1) * (dvw / 2 / CQ); c0 += RC) {
+            uint32_t orr[RC];
+            if constexpr (RC == 32) ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
             else ptx::tmem_ld_x16(tmem + lane_base + c0, orr);
             ptx::tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * factor);
-            if constexpr (CPT == 32) ptx::tmem_st_x32(tmem + lane_base + c0, orr);
+            for (int j = 0; j < RC; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * factor);
+            if constexpr (RC == 32) ptx::tmem_st_x32(tmem + lane_base + c0, orr);
             else ptx::tmem_st_x16(tmem + lane_base + c0, orr);
           }
           ptx::tmem_wait_st();
@@ -559,11 +610,36 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ptx::tc_fence_before();
         __syncwarp();
         if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(l_p_full0 + 8u * sbuf);  // p_full[] is contiguous
+        if constexpr (ALT) ++uw; else ++g;
       }
 
       // ---------------- epilogue: O / l -> global, LSE ----------------
       {
-        const uint32_t gl = g - 1;
+        float l_tot;
+        uint32_t gl;
+        if constexpr (ALT) {
+          // final running max: published with the last tile
+          const uint32_t parl = (uint32_t)(T - 1) & 3u;
+          const uint32_t cntl = pub[parl] + (uint32_t)((T - 1) >> 2);
+          ptx::mbar_wait(bar(bars.m_full[parl]), cntl & 1);
+          const float m_fin = mval[parl][row];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pub[j] += (T > j) ? (uint32_t)((T - 1 - j) / 4 + 1) : 0u;
+          const float l_fin = (m == NEG_INF) ? 0.f : l * exp2f((m - m_fin) * mul);
+          m = m_fin;
+          gl = g + (uint32_t)T - 1;
+          g += (uint32_t)T;
+          // the exchange buffer of parity 0/1 may still be read by a slower partner of the last tiles:
+          // a dedicated 128-thread barrier pair brackets its reuse for the row sums
+          ptx::named_bar_sync(5 + rgrp, 128);
+          xch[0][slot][row] = l_fin;
+          ptx::named_bar_sync(5 + rgrp, 128);
+          l_tot = (xch[0][0][row] + xch[0][1][row]) + (xch[0][2][row] + xch[0][3][row]);
+          ptx::named_bar_sync(5 + rgrp, 128);
+          ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
+          ptx::tc_fence_after();
+        } else {
+        gl = g - 1;
         ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
         ptx::tc_fence_after();
         // row-sum exchange reuses the max-exchange buffer of the last tile: every thread of the
@@ -571,8 +647,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float (*xl)[64] = xch[gl & 1];
         xl[slot][row] = l;
         ptx::named_bar_sync(1 + rgrp, kSoftmaxWarps * 16);
-        float l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
+        l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
         if constexpr (CQ == 4) l_tot += (xl[4][row] + xl[5][row]) + (xl[6][row] + xl[7][row]);
+        }
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
         const bool row_ok = gq < p.seqlen_q;
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
@@ -581,17 +658,20 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int s = 0; s < Cfg::NSLICE; ++s) {
           if (256 * s >= dvw) break;
           const int ns = Cfg::slice_n(dvw, s);
-          const int part = ns / 2 / CQ;  // columns of this slice handled by each warpgroup
+          constexpr int EG = ALT ? 2 : CQ;            // warpgroups sharing the columns of a lane
+          constexpr int EC = CPT == 16 ? 16 : 32;     // columns per TMEM load
+          const uint32_t eg = ALT ? wgi : ch;
+          const int part = ns / 2 / EG;  // columns of this slice handled by each warpgroup
 #pragma unroll 1
-          for (int c0 = (int)ch * part; c0 < (int)(ch + 1) * part; c0 += CPT) {
-            uint32_t orr[CPT];
-            if constexpr (CPT == 32) ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
+          for (int c0 = (int)eg * part; c0 < (int)(eg + 1) * part; c0 += EC) {
+            uint32_t orr[EC];
+            if constexpr (EC == 32) ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
             else ptx::tmem_ld_x16(tmem + lane_base + 128 * s + c0, orr);
             ptx::tmem_wait_ld();
             const int d0 = dv0 + 256 * s + (ns / 2) * (int)kh + c0;
             if (row_ok) {
 #pragma unroll
-              for (int v = 0; v < CPT / 8; ++v) {
+              for (int v = 0; v < EC / 8; ++v) {
                 const int d = d0 + 8 * v;
                 if (d < p.head_dim) {
                   uint32_t w[4];
@@ -607,7 +687,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
         }
-        if (p.lse != nullptr && slot == 0 && row_ok && pass == 0) {
+        if (p.lse != nullptr && wgi == 0 && kh == 0 && row_ok && pass == 0) {
           // natural-log LSE; rows without any visible key: O = 0, LSE = -inf
           const float lse = (l_tot > 0.f) ? (m * mul + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
           p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
