@@ -358,6 +358,7 @@ def main():
               "algorithmic_hbm_bytes_per_launch": int(2 * (2 * q.numel() + k.numel() + v.numel())),
               "launch_ms_mean": mean_launch_ms, "launch_ms_min": min(per_launch_ms)}
 
+  peaks = measured_peaks()
   # ---- secondary numbers of the same metric family (BASELINE.json: "attn TFLOPS (fwd, bwd)") ----
   also = None
   if world == 1 and not args.no_e2e:
@@ -388,6 +389,22 @@ def main():
       also[name] = {"fwd_ms": ms_f, "fwd_tflops": f2 / ms_f * 1e-9, "bwd_ms": ms_b,
                     "bwd_tflops": 2.5 * f2 / ms_b * 1e-9, "bwd_flops_rule": "2.5 x fwd (reference _flops.py:57-76)"}
       del qg, kg, vg, o2, do2
+    # BASELINE config 4: FP8 forward, B=4 H=32 N=8192 D=256 (quantise pre-pass + attention timed together)
+    try:
+      torch.manual_seed(11)
+      q8 = torch.randn(4, 32, 8192, 256, dtype=dt, device=dev) * 0.5
+      k8 = torch.randn(4, 32, 8192, 256, dtype=dt, device=dev) * 0.5
+      v8 = torch.randn(4, 32, 8192, 256, dtype=dt, device=dev) * 0.5
+      f8 = flops_of(4, 32, 8192, 8192, 256, False)
+      be = ffpa_attn.CUDABackend(enable_fp8=True)
+      ms8 = _t(lambda: ffpa_attn.ffpa_attn_func(q8, k8, v8, forward_backend=be), 10)
+      ms16 = _t(lambda: ffpa_attn.ffpa_attn_func(q8, k8, v8), 10)
+      also["c4_fp8_fwd_b4h32n8192d256"] = {"fp8_ms": ms8, "fp8_tflops": f8 / ms8 * 1e-9, "bf16_ms": ms16,
+                                          "bf16_tflops": f8 / ms16 * 1e-9,
+                                          "fp8_peak_tflops": 2 * peaks["burst"], "fp8_frac": f8 / ms8 * 1e-9 / (2 * peaks["burst"])}
+      del q8, k8, v8
+    except Exception as e:  # noqa: BLE001
+      also["c4_fp8_fwd_b4h32n8192d256"] = {"error": str(e)}
 
   # ---- CPU baseline on this box's host cores (bounded sample) ----
   cpu = None
