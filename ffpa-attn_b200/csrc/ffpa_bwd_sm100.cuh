@@ -53,6 +53,10 @@ struct BwdCfg {
   static constexpr int NST = kRaw > 12 ? 12 : kRaw;        // unified ring of 16 KB stages
   static constexpr int SMEM_DYN = NA * A_BYTES + T_BYTES + NST * 16384;
   static_assert(NST >= 3, "not enough shared memory for the streaming ring");
+  // WIDE: accumulate with N=256 MMAs (a slice = two consecutive ring stages): T is re-read from SMEM 2x
+  // instead of 4x per tile. With N=128 everywhere the operand fetch needs 125 B/clk of the 128 B/clk SMEM
+  // port (A 2 KB + B 2 KB per 32-cycle MMA), which is what limits these kernels.
+  static constexpr bool WIDE = (NSL % 2 == 0) && (NST % 2 == 0) && (HAS_DP || KST % 2 == 0);
   static_assert(ACC_COLS <= 256, "backward kernels support head_dim <= 512");
 };
 
@@ -214,7 +218,9 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           ptx::mbar_wait(bar(bars.r_empty[stage]), (n & 1) ^ 1);
           if (rank == 0) ptx::mbar_expect_tx(bar(bars.r_full[stage]), 2 * 16384);
           const uint32_t l_full = ptx::mapa(bar(bars.r_full[stage]), 0);
-          ptx::tma_load_4d_2sm(sR + stage * 16384, m, l_full, 128 * s + 64 * (int)rank, c_row0, hh, bb);
+          // WIDE: stage pair (s & ~1, s | 1) = N=256 slice s/2, this CTA's 128 columns as two 64-wide boxes
+          const int dcol = Cfg::WIDE ? 256 * (s >> 1) + 128 * (int)rank + 64 * (s & 1) : 128 * s + 64 * (int)rank;
+          ptx::tma_load_4d_2sm(sR + stage * 16384, m, l_full, dcol, c_row0, hh, bb);
           ++rc;
         }
       };
@@ -305,6 +311,24 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             ptx::tc_fence_after();
 #pragma unroll
             for (int s = 0; s < Cfg::NSL; ++s) {
+              if constexpr (Cfg::WIDE) {
+                if (s & 1) continue;  // handled together with the even stage
+                const uint32_t st = rc % Cfg::NST, n = rc / Cfg::NST;
+                ptx::mbar_wait(bar(bars.r_full[st]), n & 1);
+                ptx::mbar_wait(bar(bars.r_full[st + 1]), n & 1);
+                ptx::tc_fence_after();
+                constexpr uint32_t idesc_acc2 = ptx::make_idesc(fmt, fmt, 0, 1, 128, 256);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                  const uint64_t ad = ptx::make_smem_desc_sw128(sT + tbuf * 16384 + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
+                  const uint64_t bd = ptx::make_smem_desc_sw128(sR + st * 16384 + kk * 2048, 16384, 1024);
+                  ptx::umma_f16_ss<CG>(tmem + 64 * s, ad, bd, idesc_acc2, (step > 1 || kk > 0) ? 1u : 0u);
+                }
+                ptx::umma_commit_mc<CG>(bar(bars.r_empty[st]), 0x3);
+                ptx::umma_commit_mc<CG>(bar(bars.r_empty[st + 1]), 0x3);
+                rc += 2;
+                continue;
+              }
               const uint32_t stage = rc % Cfg::NST, n = rc / Cfg::NST;
               ptx::mbar_wait(bar(bars.r_full[stage]), n & 1);
               ptx::tc_fence_after();
@@ -483,7 +507,10 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           uint32_t orr[32];
           ptx::tmem_ld_x32(tmem + lane_base + 64 * s + 32 * ch, orr);
           ptx::tmem_wait_ld();
-          const int d0 = 128 * s + 64 * (int)kh + 32 * (int)ch;
+          // TMEM column 64 s + 32 ch + j of lane half kh: N=128 slices -> d = 128 s + 64 kh + 32 ch + j;
+          // N=256 slices (WIDE) -> column c = 64 (s & 1) + 32 ch + j of slice s/2 -> d = 256 (s/2) + 128 kh + c
+          const int d0 = Cfg::WIDE ? 256 * (s >> 1) + 128 * (int)kh + 64 * (s & 1) + 32 * (int)ch
+                                   : 128 * s + 64 * (int)kh + 32 * (int)ch;
           if (row_ok && p.out32 != nullptr) {
             // split mode: accumulate this chunk's partial result (fp32, [B, H, rows, D] contiguous)
             float* dst = p.out32 + (((int64_t)b * heads_it + hs) * p.out_rows + grow) * (int64_t)p.head_dim;
