@@ -169,7 +169,7 @@ int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream) {
 
 uint64_t ffpa_b200_fwd_workspace_bytes(int32_t batch, int32_t heads_q, int32_t heads_kv, int32_t seqlen_q,
                                        int32_t seqlen_kv, int32_t head_dim, int32_t fp8) {
-  if (!fp8) return 0;
+  if (!fp8) return fwd_split_workspace_bytes(batch, heads_q, seqlen_q, seqlen_kv, head_dim);  // KV-split partials (decode-like shapes), else 0
   return fwd_fp8_workspace_bytes(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
 }
 

@@ -120,6 +120,30 @@ __device__ __forceinline__ int next_item(const FwdKernelParams& p, uint32_t clus
   return item < (uint32_t)p.n_items ? (int)item : -1;
 }
 
+// decoded work item. With kv_splits > 1 (few query tiles, long KV: decode-like shapes) an item covers only
+// the KV tiles [tbeg, tbeg + T) and writes an fp32 partial (O_s, LSE_s) that merge_splits_kernel combines.
+struct FwdItem { int mt, pass, bh, split, tbeg, T; };
+template <int NPASS>
+__device__ __forceinline__ FwdItem decode_fwd_item(const FwdKernelParams& p, uint32_t item) {
+  FwdItem it;
+  it.mt = item % p.n_mtiles;
+  uint32_t rest = item / p.n_mtiles;
+  it.pass = rest % NPASS;
+  rest /= NPASS;
+  it.split = rest % p.kv_splits;
+  it.bh = rest / p.kv_splits;
+  const int ttot = num_kv_tiles(p, it.mt * 128);
+  if (p.kv_splits == 1) { it.tbeg = 0; it.T = ttot; }
+  else {
+    const int per = (ttot + p.kv_splits - 1) / p.kv_splits;
+    it.tbeg = it.split * per;
+    int n = ttot - it.tbeg;
+    n = n < 0 ? 0 : n;
+    it.T = n < per ? n : per;
+  }
+  return it;
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr) {
   // Philox-4x32-10, counter = (ctr_lo, ctr_hi, 0, 0), key = seed. Same generator as
   // /root/reference/csrc/cuffpa/native/prefill.cuh:398-422 (and curand / torch SDPA).
@@ -228,13 +252,13 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int item_s = next_item(p, cluster, nclusters, kidx);
         if (item_s < 0) break;
         const uint32_t item = (uint32_t)item_s;
-        const int mt = item % p.n_mtiles;
-        const int pass = (item / p.n_mtiles) % Cfg::NPASS;
-        const int bh = item / (p.n_mtiles * Cfg::NPASS);
+        const FwdItem fi = decode_fwd_item<Cfg::NPASS>(p, item);
+        const int mt = fi.mt, pass = fi.pass, bh = fi.bh;
         const int h = bh % p.heads_q, b = bh / p.heads_q;
         const int hk = h / group;
         const int q0 = mt * 128;
-        const int T = num_kv_tiles(p, q0);
+        const int T = fi.T, tbeg = fi.tbeg;
+        if (T <= 0) { --it; continue; }   // empty KV split: no barrier traffic (the for-increment re-adds 1)
         const int dv0 = pass * Cfg::DSLAB, dvw = Cfg::slab_w(pass);
         ptx::mbar_wait(bar(bars.q_empty), (it & 1) ^ 1);
         if (rank == 0) ptx::mbar_expect_tx(bar(bars.q_full), 2 * Cfg::Q_BYTES);
@@ -243,7 +267,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           ptx::tma_load_4d_2sm(sQ + jb * 8192, &map_q, l_q_full, jb * 64, q0 + 64 * (int)rank, h, b);
         for (int step = 0; step < T + LA; ++step) {
           if (step < T) {
-            const int kv0 = step * 128;
+            const int kv0 = (tbeg + step) * 128;
 #pragma unroll
             for (int ks = 0; ks < Cfg::KST; ++ks) {
               const uint32_t stage = kc % Cfg::NKS, n = kc / Cfg::NKS;
@@ -264,7 +288,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
           if (step >= LA) {
-            const int kv0 = (step - LA) * 128;
+            const int kv0 = (tbeg + step - LA) * 128;
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
               if (256 * s >= dvw) break;
@@ -311,10 +335,10 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int item_s = next_item(p, cluster, nclusters, kidx);
         if (item_s < 0) break;
         const uint32_t item = (uint32_t)item_s;
-        const int mt = item % p.n_mtiles;
-        const int pass = (item / p.n_mtiles) % Cfg::NPASS;
-        const int dvw = Cfg::slab_w(pass);
-        const int T = num_kv_tiles(p, mt * 128);
+        const FwdItem fi = decode_fwd_item<Cfg::NPASS>(p, item);
+        const int dvw = Cfg::slab_w(fi.pass);
+        const int T = fi.T;
+        if (T <= 0) { --it; continue; }
         ptx::mbar_wait(bar(bars.q_full), it & 1);
         ptx::tc_fence_after();
         for (int step = 0; step < T + LA; ++step) {
@@ -416,16 +440,21 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int item_s = next_item(p, cluster, nclusters, kidx);
       if (item_s < 0) break;
       const uint32_t item = (uint32_t)item_s;
-      const int mt = item % p.n_mtiles;
-      const int pass = (item / p.n_mtiles) % Cfg::NPASS;
-      const int bh = item / (p.n_mtiles * Cfg::NPASS);
+      const FwdItem fi = decode_fwd_item<Cfg::NPASS>(p, item);
+      const int mt = fi.mt, pass = fi.pass, bh = fi.bh;
       const int h = bh % p.heads_q, b = bh / p.heads_q;
       const int q0 = mt * 128;
-      const int T = num_kv_tiles(p, q0);
+      const int T = fi.T, tbeg = fi.tbeg;
       const int dv0 = pass * Cfg::DSLAB, dvw = Cfg::slab_w(pass);
       const int gq = q0 + 64 * (int)rank + (int)row;  // global query row of this thread
       const int causal_lim = gq + (p.seqlen_kv - p.seqlen_q);  // last visible key when causal
       float m = NEG_INF, l = 0.f;   // ALT: m = the max this thread's partial sum l is expressed against
+      if (T <= 0) {
+        // empty KV split (causal rows that end before this split starts): contributes nothing
+        if (p.part_lse != nullptr && wgi == 0 && kh == 0 && gq < p.seqlen_q)
+          p.part_lse[(((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq] = NEG_INF;
+        continue;
+      }
 
       for (int i = ALT ? (int)wgi : 0; i < T; i += ALT ? 2 : 1) {
         const uint32_t gi = ALT ? g + (uint32_t)i : g;   // global index of this tile
@@ -441,7 +470,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         else ptx::tmem_ld_x16(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + CPT * ch, sr);
         ptx::tmem_wait_ld();
         float x[CPT];
-        const int key0 = i * 128 + 64 * (int)kh + CPT * (int)ch;
+        const int ti = tbeg + i;   // absolute KV tile index
+        const int key0 = ti * 128 + 64 * (int)kh + CPT * (int)ch;
         if constexpr (MODE == kModeFast) {
 #pragma unroll
           for (int j = 0; j < CPT; ++j) x[j] = __uint_as_float(sr[j]);
@@ -465,8 +495,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
         }
-        const bool tail = (i * 128 + 128 > p.seqlen_kv);
-        const bool diag = p.causal && (i * 128 + 127 > q0 + (p.seqlen_kv - p.seqlen_q));
+        const bool tail = (ti * 128 + 128 > p.seqlen_kv);
+        const bool diag = p.causal && (ti * 128 + 127 > q0 + (p.seqlen_kv - p.seqlen_q));
         if (tail || diag) {
           const int lim = p.causal ? (causal_lim < p.seqlen_kv - 1 ? causal_lim : p.seqlen_kv - 1) : p.seqlen_kv - 1;
 #pragma unroll
@@ -674,6 +704,15 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               for (int v = 0; v < EC / 8; ++v) {
                 const int d = d0 + 8 * v;
                 if (d < p.head_dim) {
+                  if (p.kv_splits > 1) {
+                    // fp32 partial of this KV split, normalised by its own row sum
+                    float* po = p.part_o + ((((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq) * (int64_t)p.head_dim + d;
+                    *reinterpret_cast<float4*>(po) = make_float4(__uint_as_float(orr[8 * v]) * inv, __uint_as_float(orr[8 * v + 1]) * inv,
+                                                                 __uint_as_float(orr[8 * v + 2]) * inv, __uint_as_float(orr[8 * v + 3]) * inv);
+                    *reinterpret_cast<float4*>(po + 4) = make_float4(__uint_as_float(orr[8 * v + 4]) * inv, __uint_as_float(orr[8 * v + 5]) * inv,
+                                                                     __uint_as_float(orr[8 * v + 6]) * inv, __uint_as_float(orr[8 * v + 7]) * inv);
+                    continue;
+                  }
                   uint32_t w[4];
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
@@ -687,10 +726,11 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
         }
-        if (p.lse != nullptr && wgi == 0 && kh == 0 && row_ok && pass == 0) {
+        if ((p.lse != nullptr || p.kv_splits > 1) && wgi == 0 && kh == 0 && row_ok && pass == 0) {
           // natural-log LSE; rows without any visible key: O = 0, LSE = -inf
           const float lse = (l_tot > 0.f) ? (m * mul + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
-          p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
+          if (p.kv_splits > 1) p.part_lse[(((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq] = lse;
+          else p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
         }
         ptx::tc_fence_before();
       }
@@ -700,6 +740,59 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   ptx::tc_fence_before();
   ptx::cluster_sync();
   if (warp == kMmaWarp) ptx::tmem_dealloc<CG>(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// KV-split merge: O = sum_s w_s O_s / sum_s w_s with w_s = exp(LSE_s - max LSE), LSE = max + log(sum w_s)
+// (the split-KV stage 2 of the reference's decode path, csrc/cuffpa/native/sm_80/split_kv.cuh:330-455).
+// One warp per (b, h, q) row.
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void merge_splits_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
+                                    void* __restrict__ o, float* __restrict__ lse, int64_t os0, int64_t os1, int64_t os2,
+                                    int B, int H, int Nq, int D, int S) {
+  const int64_t rowid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t rows = (int64_t)B * H * Nq;
+  if (rowid >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int q = (int)(rowid % Nq);
+  const int h = (int)((rowid / Nq) % H);
+  const int b = (int)(rowid / ((int64_t)Nq * H));
+  float mx = -INFINITY;
+  for (int s = 0; s < S; ++s) mx = fmaxf(mx, part_lse[(int64_t)s * rows + rowid]);
+  float den = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float l = part_lse[(int64_t)s * rows + rowid];
+    den += (l == -INFINITY) ? 0.f : __expf(l - mx);
+  }
+  const float inv = den > 0.f ? 1.f / den : 0.f;
+  uint8_t* orow = reinterpret_cast<uint8_t*>(o) + 2 * (b * os0 + h * os1 + (int64_t)q * os2);
+  for (int d = lane * 2; d < D; d += 64) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float l = part_lse[(int64_t)s * rows + rowid];
+      if (l == -INFINITY) continue;
+      const float w = __expf(l - mx) * inv;
+      const float2 v = *reinterpret_cast<const float2*>(part_o + ((int64_t)s * rows + rowid) * D + d);
+      a0 = fmaf(w, v.x, a0);
+      a1 = fmaf(w, v.y, a1);
+    }
+    *reinterpret_cast<uint32_t*>(orow + 2 * d) = BF16 ? ptx::pack_bf16x2(a0, a1) : ptx::pack_f16x2(a0, a1);
+  }
+  if (lse != nullptr && lane == 0) lse[rowid] = den > 0.f ? mx + __logf(den) : -INFINITY;
+}
+
+template <bool BF16>
+int launch_merge_splits(const float* part_o, const float* part_lse, void* o, float* lse, const int64_t* ostride, int B,
+                        int H, int Nq, int D, int S, cudaStream_t stream) {
+  const int64_t rows = (int64_t)B * H * Nq;
+  const int wpb = 4;
+  merge_splits_kernel<BF16><<<dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream>>>(
+      part_o, part_lse, o, lse, ostride[0], ostride[1], ostride[2], B, H, Nq, D, S);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "split merge launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return FFPA_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -23,6 +23,10 @@ struct FwdKernelParams {
   // -1 terminates; nullptr -> static round robin item = cluster + k * nclusters
   const int* sched;
   int sched_stride;
+  // KV splits (decode-like shapes): fp32 partials [S, B, Hq, Nq, D] / [S, B, Hq, Nq]; kv_splits == 1: off
+  int kv_splits;
+  float* part_o;
+  float* part_lse;
 };
 
 namespace bwd {
@@ -64,6 +68,8 @@ int sm_count();
 int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream);
 int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream);
 int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream);
+int fwd_kv_splits(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim);  // 1 = no split
+uint64_t fwd_split_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim);
 uint64_t fwd_fp8_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim);
 uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv,
                              int head_dim);

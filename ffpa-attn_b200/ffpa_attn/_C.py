@@ -219,6 +219,13 @@ def ffpa_attn_forward(Q, K, V, attn_bias, O, softmax_lse, stages, acc, causal, s
   p.philox_seed = int(philox_seed) & 0xFFFFFFFFFFFFFFFF
   p.philox_offset = int(philox_offset) & 0xFFFFFFFFFFFFFFFF
   ws = None
+  if not p.fp8:
+    # decode-like shapes (few query tiles, long KV) use KV splits: fp32 partials live in this scratch
+    nbytes = int(_lib.ffpa_b200_fwd_workspace_bytes(p.batch, p.heads_q, p.heads_kv, p.seqlen_q,
+                                                     p.seqlen_kv, p.head_dim, 0))
+    if nbytes > 0:
+      ws = torch.empty(nbytes, dtype=torch.uint8, device=Q.device)
+      p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
   if p.fp8:
     # FP8 path (backend hint CUTE_TMA_FP8): scratch for the e4m3 copies of Q/K/V and their scales.
     # The fp8_* knobs of the reference signature select sm_120 variants (per-thread scales, int8 QK,

@@ -219,3 +219,23 @@ def test_backward_rejects_unsupported():
   out = ffpa_attn.ffpa_attn_func(q, k, v)
   with pytest.raises(NotImplementedError):
     out.backward(d_o)
+
+
+@pytest.mark.parametrize("Nq", [1, 2, 3, 4, 7])
+def test_backward_decode_like_query_lengths(Nq):  # tests/test_ffpa_bwd.py:637-640
+  q, k, v, d_o = _mk(2, 4, 2, Nq, 700, 512, torch.bfloat16, seed=8)
+  _check_against_oracle(q, k, v, d_o, False, torch.bfloat16, enable_gqa=True)
+  _check_against_oracle(q, k, v, d_o, True, torch.bfloat16, enable_gqa=True, tol=1e-1)
+
+
+def test_backward_long_sequence_sampled_head():
+  """tests/test_ffpa_bwd.py:900-907 go up to (1, 16, 16384, 512); here one head of N=8192 D=512 against an
+  fp32 torch restatement on the GPU (tolerance of the reference for large bf16: 1e-1)."""
+  q, k, v, d_o = _mk(1, 2, 2, 8192, 8192, 512, torch.bfloat16, seed=9)
+  _, dq, dk, dv = _grads(q, k, v, d_o)
+  rq, rk, rv = _torch_ref_grads(q[:, :1], k[:, :1], v[:, :1], d_o[:, :1], False)
+  for got, want, name in ((dq[:, :1], rq, "dQ"), (dk[:, :1], rk, "dK"), (dv[:, :1], rv, "dV")):
+    err = (got.float() - want).abs().max().item()
+    assert err < 1e-1 * max(1.0, want.abs().max().item()), f"{name}: {err}"
+    cos = torch.nn.functional.cosine_similarity(got.float().flatten(), want.flatten(), dim=0).item()
+    assert cos > 0.999, f"{name}: cosine {cos}"

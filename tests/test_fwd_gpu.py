@@ -346,3 +346,56 @@ def test_large_headdims(D, causal):  # tests/test_ffpa_fwd.py:1226-1249 includes
   out = _run(q, k, v, is_causal=causal)
   ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), causal=causal)
   _check(out, ref, 2e-2, f"D={D}")
+
+
+@pytest.mark.parametrize("H", [8, 16, 48])
+@pytest.mark.parametrize("D", [64, 192, 320, 576, 640])
+def test_dispatch_smoke_heads_by_headdim(H, D):  # tests/test_ffpa_fwd.py:44-45 (H x D dispatch grid)
+  q, k, v = _mk(1, H, H, 160, 160, D, torch.float16, seed=H + D)
+  out = _run(q, k, v)
+  hs = [0, H // 2, H - 1]
+  ref, _ = orc.attention_fwd(q[:, hs].cpu(), k[:, hs].cpu(), v[:, hs].cpu())
+  _check(out[:, hs], ref, 1e-2, f"H={H} D={D}")
+
+
+@pytest.mark.parametrize("Nq,Nkv", [(8191, 8192), (1, 4096), (4095, 5000)])
+def test_cross_attention_long_sampled(Nq, Nkv):  # tests/test_ffpa_fwd.py:1110-1120
+  q, k, v = _mk(1, 2, 2, Nq, Nkv, 512, torch.bfloat16, seed=7)
+  out = _run(q, k, v)
+  rows = sorted({0, Nq // 3, Nq - 1})
+  _sampled_rows_check(q, k, v, out, rows, [(0, 0), (0, 1)], False, 1e-2)
+  outc = _run(q, k, v, is_causal=True)
+  _sampled_rows_check(q, k, v, outc, rows, [(0, 1)], True, 1e-2)
+
+
+@pytest.mark.parametrize("Nq,Nkv,Hq,Hkv,causal", [(1, 8192, 32, 32, False), (1, 4096, 16, 4, False), (4, 5000, 8, 8, True),
+                                                   (7, 3000, 4, 2, True), (130, 4096, 2, 2, True)])
+def test_decode_like_shapes_use_kv_splits(Nq, Nkv, Hq, Hkv, causal):
+  """Few query rows, long KV (tests/test_ffpa_fwd.py:1110-1120 has (1, 4096)): the launcher splits the KV
+  range over clusters and merges fp32 partials (reference: split-KV decode, native/sm_80/split_kv.cuh)."""
+  import ffpa_attn
+
+  q, k, v = _mk(1, Hq, Hkv, Nq, Nkv, 512, torch.bfloat16, seed=3)
+  n0 = ffpa_attn._C.launch_count()
+  o, lse = _lse(q, k, v, causal=causal)
+  assert ffpa_attn._C.launch_count() - n0 == 2, "expected split kernel + merge kernel"
+  hs = [0, Hq - 1]
+  g = Hq // Hkv
+  for h in hs:
+    ref, lref = orc.attention_fwd(q[:, h:h + 1].cpu(), k[:, h // g:h // g + 1].cpu(), v[:, h // g:h // g + 1].cpu(), causal=causal)
+    assert np.abs(o[:, h:h + 1].float().cpu().numpy() - ref).max() < 1e-2
+    assert np.abs(lse[:, h:h + 1].cpu().numpy() - lref).max() < 2e-3
+
+
+def test_kv_split_with_bias_and_dropout_matches_oracle():
+  q, k, v = _mk(1, 2, 2, 3, 2048, 256, torch.bfloat16, seed=4)
+  bias = torch.randn(1, 2, 3, 2048)
+  out = _run(q, k, v, attn_mask=bias.to(DEV))
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), bias=bias.double().numpy())
+  _check(out, ref, 2e-2, "split+bias")
+  seed, offset = 99, 12
+  o, _ = torch.ops.ffpa_attn._fwd_cuda(q, k, v, q.new_empty(0), 0, 1, 0, 256 ** -0.5, 0.25, seed, offset, True, False,
+                                       0, 0, 0, 0, 0, False, 256, False, 256)
+  torch.cuda.synchronize()
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), dropout_p=0.25, philox_seed=seed, philox_offset=offset)
+  _check(o, ref, 4e-2, "split+dropout")

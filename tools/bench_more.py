@@ -26,6 +26,8 @@ CASES = [
   ("d768", 1, 32, 32, 8192, 8192, 768, False),
   ("d1024", 1, 32, 32, 8192, 8192, 1024, False),
   ("c4_b4_d256", 4, 32, 32, 8192, 8192, 256, False),
+  ("decode_nq1_n8192_d512", 1, 32, 32, 1, 8192, 512, False),
+  ("decode_nq1_b8_gqa_n16384_d512", 8, 32, 8, 1, 16384, 512, False),
 ]
 
 
@@ -61,7 +63,10 @@ def main():
     f = flops(B, Hq, Nq, Nkv, D, causal)
     ms_f = timeit(lambda: ffpa_attn.ffpa_attn_func(q, k, v, **kw), 10)
     rec = {"case": name, "fwd_ms": ms_f, "fwd_tflops": f / ms_f * 1e-9}
-    if D <= 512:
+    if name.startswith("decode"):
+      kv_bytes = 2 * k.numel() * 2  # K and V are each read once: the HBM roofline of decode
+      rec.update({"kv_gbs": kv_bytes / ms_f * 1e-6, "hbm_peak_gbs": 6580.9})
+    if D <= 512 and not name.startswith("decode"):
       qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
       out = ffpa_attn.ffpa_attn_func(qg, kg, vg, **kw)
       d_o = torch.randn_like(out)
