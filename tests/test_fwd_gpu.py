@@ -399,3 +399,34 @@ def test_kv_split_with_bias_and_dropout_matches_oracle():
   torch.cuda.synchronize()
   ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), dropout_p=0.25, philox_seed=seed, philox_offset=offset)
   _check(o, ref, 4e-2, "split+dropout")
+
+
+def test_cuda_graph_capture_and_side_stream():
+  """The launcher does no host synchronisation and launches on the caller's current stream
+  (reference contract: native/launch.cuh:303-304), so it can be captured into a CUDA graph and run on a side
+  stream. (Causal shapes upload their schedule table on first use: warm up once before capturing.)"""
+  import ffpa_attn
+
+  q, k, v = _mk(2, 4, 2, 384, 640, 512, torch.bfloat16, seed=12)
+  kw = dict(is_causal=True, enable_gqa=True)
+  eager = ffpa_attn.ffpa_attn_func(q, k, v, **kw)  # warm-up: smem attribute, schedule table
+  torch.cuda.synchronize()
+  s = torch.cuda.Stream()
+  with torch.cuda.stream(s):
+    side = ffpa_attn.ffpa_attn_func(q, k, v, **kw)
+  s.synchronize()
+  assert torch.equal(side, eager)
+  g = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(g):
+    captured = ffpa_attn.ffpa_attn_func(q, k, v, **kw)
+  captured.zero_()
+  g.replay()
+  torch.cuda.synchronize()
+  assert torch.equal(captured, eager)
+
+
+def test_large_batch_many_items():
+  q, k, v = _mk(48, 4, 4, 256, 256, 128, torch.float16, seed=13)
+  out = _run(q, k, v, is_causal=True)
+  ref, _ = orc.attention_fwd(q[[0, 47]].cpu(), k[[0, 47]].cpu(), v[[0, 47]].cpu(), causal=True)
+  _check(out[[0, 47]], ref, 1e-2)
