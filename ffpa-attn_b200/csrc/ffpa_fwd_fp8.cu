@@ -8,7 +8,7 @@ static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a
 
 struct Fp8Layout {
   int dpad, tq, tk;
-  uint64_t off_q8, off_k8, off_v8, off_qs, off_ks, off_vs, off_vref, total;
+  uint64_t off_q8, off_k8, off_v8, off_qs, off_ks, off_vs, off_vref, off_ksum, off_qkm, total;
 };
 
 static Fp8Layout fp8_layout(int B, int Hq, int Hkv, int Nq, int Nkv, int D) {
@@ -24,6 +24,8 @@ static Fp8Layout fp8_layout(int B, int Hq, int Hkv, int Nq, int Nkv, int D) {
   L.off_ks = o; o = align_up(o + (uint64_t)B * Hkv * L.tk * 4, 256);
   L.off_vs = o; o = align_up(o + (uint64_t)B * Hkv * L.tk * 4, 256);
   L.off_vref = o; o = align_up(o + (uint64_t)B * Hkv * 4, 256);
+  L.off_ksum = o; o = align_up(o + (uint64_t)B * Hkv * D * 4, 256);
+  L.off_qkm = o; o = align_up(o + (uint64_t)B * Hq * Nq * 4, 256);
   L.total = o;
   return L;
 }
@@ -83,10 +85,36 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   qa.batch = B; qa.head_dim = D; qa.dpad = L.dpad;
   cudaError_t e = cudaMemsetAsync(qa.vref, 0, (size_t)B * Hkv * 4, stream);
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  // smooth-K (a.fp8 bit 1; the reference's default, functional.py:246): quantise K - mean_seq(K) and shift
+  // the LSE back by scale * q . mean
+  const bool smooth_k = (a.fp8 & 2) != 0;
+  float* ksum = reinterpret_cast<float*>(ws + L.off_ksum);
+  float* qkm = reinterpret_cast<float*>(ws + L.off_qkm);
+  qa.ksum = nullptr;
+  if (smooth_k) {
+    e = cudaMemsetAsync(ksum, 0, (size_t)B * Hkv * D * 4, stream);
+    if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    const int rpb = 256;
+    const unsigned nblk = (unsigned)((Nkv + rpb - 1) / rpb) * Hkv * B;
+    if (a.dtype == FFPA_DTYPE_BF16)
+      fp8::k_colsum_kernel<true><<<nblk, 256, 0, stream>>>(a.k, ksum, a.k_stride[0], a.k_stride[1], a.k_stride[2], Hkv, Nkv, D, rpb);
+    else
+      fp8::k_colsum_kernel<false><<<nblk, 256, 0, stream>>>(a.k, ksum, a.k_stride[0], a.k_stride[1], a.k_stride[2], Hkv, Nkv, D, rpb);
+    const unsigned qblk = (unsigned)(((int64_t)B * Hq * Nq + 7) / 8);
+    if (a.dtype == FFPA_DTYPE_BF16)
+      fp8::q_dot_kmean_kernel<true><<<qblk, 256, 0, stream>>>(a.q, ksum, qkm, a.q_stride[0], a.q_stride[1], a.q_stride[2], B, Hq, Hkv, Nq, Nkv, D);
+    else
+      fp8::q_dot_kmean_kernel<false><<<qblk, 256, 0, stream>>>(a.q, ksum, qkm, a.q_stride[0], a.q_stride[1], a.q_stride[2], B, Hq, Hkv, Nq, Nkv, D);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "smooth-K pre-pass launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    count_launch();
+    qa.ksum = ksum;
+  }
   if (a.dtype == FFPA_DTYPE_BF16)
-    fp8::quantize_e4m3_kernel<true><<<dim3((unsigned)qa.first_block[3]), dim3(256), 0, stream>>>(qa);
+    fp8::quantize_e4m3_kernel<true><<<dim3((unsigned)qa.first_block[3]), dim3(fp8::kQuantThreads), 0, stream>>>(qa);
   else
-    fp8::quantize_e4m3_kernel<false><<<dim3((unsigned)qa.first_block[3]), dim3(256), 0, stream>>>(qa);
+    fp8::quantize_e4m3_kernel<false><<<dim3((unsigned)qa.first_block[3]), dim3(fp8::kQuantThreads), 0, stream>>>(qa);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "fp8 quantise launch failed: %s", cudaGetErrorString(e));
   count_launch();
@@ -100,6 +128,7 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   kp.o = a.o; kp.lse = a.lse;
   for (int i = 0; i < 3; ++i) kp.o_stride[i] = a.o_stride[i];
   kp.qs = qa.scale[0]; kp.ks = qa.scale[1]; kp.vs = qa.scale[2]; kp.vref = qa.vref;
+  kp.qkm = smooth_k ? qkm : nullptr;
   kp.tq = L.tq; kp.tk = L.tk;
   kp.batch = B; kp.heads_q = Hq; kp.heads_kv = Hkv; kp.seqlen_q = Nq; kp.seqlen_kv = Nkv; kp.head_dim = D;
   kp.causal = a.causal;

@@ -39,6 +39,7 @@ struct Fp8KernelParams {
   const float* ks;     // [B, Hkv, TK]
   const float* vs;     // [B, Hkv, TK]
   const float* vref;   // [B, Hkv]
+  const float* qkm;    // [B, Hq, Nq]  q . mean_seq(K) (smooth-K LSE correction) or nullptr
   int tq, tk;
   int batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
   int causal;
@@ -473,7 +474,11 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
         if (p.lse != nullptr && wg == 0 && kh == 0 && row_ok) {
-          const float lse = (l_tot > 0.f) ? (m_fin + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
+          // smooth-K: the kernel saw S' = Q (K - mean)^T, i.e. S shifted by the row constant q . mean;
+          // softmax and O are invariant, the LSE is shifted back (reference: cute/launch.cuh:602-635)
+          const int64_t ridx = ((int64_t)b * p.heads_q + h) * p.seqlen_q + gq;
+          const float corr = p.qkm != nullptr ? p.qkm[ridx] * (p.scale_log2 * 0.6931471805599453f) : 0.f;
+          const float lse = (l_tot > 0.f) ? (m_fin + log2f(l_tot)) * 0.6931471805599453f + corr : NEG_INF;
           p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
         }
         ptx::tc_fence_before();
@@ -503,11 +508,15 @@ struct QuantArgs {
   int heads[3], seqlen[3], tiles[3];
   int64_t first_block[4];  // prefix sums of blocks per tensor
   int batch, head_dim, dpad;
+  const float* ksum;       // [B, Hkv, D] column sums of K over the sequence (smooth-K) or nullptr
 };
 
+// One 1024-thread block per (tensor, b, h, 128-row block): the tile (<= 128 x 512 x 2 B) is read from HBM
+// once and lives in registers (8 x 16 B per thread) between the amax reduction and the conversion.
+constexpr int kQuantThreads = 1024;
 template <bool BF16>
-__global__ void __launch_bounds__(256) quantize_e4m3_kernel(const QuantArgs a) {
-  __shared__ float red[8];
+__global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const QuantArgs a) {
+  __shared__ float red[32];
   const int64_t blk = blockIdx.x;
   const int which = blk >= a.first_block[2] ? 2 : (blk >= a.first_block[1] ? 1 : 0);
   const int64_t local = blk - a.first_block[which];
@@ -522,18 +531,36 @@ __global__ void __launch_bounds__(256) quantize_e4m3_kernel(const QuantArgs a) {
   const int r0 = tile * 128;
   const int rows = (N - r0) < 128 ? (N - r0) : 128;
   const int vec_per_row = D / 8;               // 8 elements (16 B) per vector; D % 8 == 0
-  const int nvec = rows * vec_per_row;
-  float amax = 0.f;
-  for (int i = threadIdx.x; i < nvec; i += 256) {
-    const int r = i / vec_per_row, c = i % vec_per_row;
-    const uint4 v = *reinterpret_cast<const uint4*>(src + 2 * ((int64_t)(r0 + r) * rs + 8 * c));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const int nvec = rows * vec_per_row;         // <= 128 * 64 = 8 * 1024
+  // smooth-K: quantise K - mean_seq(K) (per (b, h) and channel)
+  const float* km = (which == 1 && a.ksum != nullptr) ? a.ksum + ((int64_t)b * H + h) * D : nullptr;
+  const float inv_n = 1.f / (float)N;
+  constexpr int MAXV = 8;
+  uint4 cache[MAXV];
+  auto expand = [&](const uint4& raw, int c, float* f) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      float f0, f1;
-      if (BF16) { f0 = __uint_as_float(w[u] << 16); f1 = __uint_as_float(w[u] & 0xffff0000u); }
-      else { const __half2 hh = *reinterpret_cast<const __half2*>(&w[u]); f0 = __low2float(hh); f1 = __high2float(hh); }
-      amax = fmaxf(amax, fmaxf(fabsf(f0), fabsf(f1)));
+      if (BF16) { f[2 * u] = __uint_as_float(w[u] << 16); f[2 * u + 1] = __uint_as_float(w[u] & 0xffff0000u); }
+      else { const __half2 hh = *reinterpret_cast<const __half2*>(&w[u]); f[2 * u] = __low2float(hh); f[2 * u + 1] = __high2float(hh); }
+    }
+    if (km != nullptr) {
+      const float4 k0 = __ldg(reinterpret_cast<const float4*>(km + 8 * c)), k1 = __ldg(reinterpret_cast<const float4*>(km + 8 * c + 4));
+      f[0] -= k0.x * inv_n; f[1] -= k0.y * inv_n; f[2] -= k0.z * inv_n; f[3] -= k0.w * inv_n;
+      f[4] -= k1.x * inv_n; f[5] -= k1.y * inv_n; f[6] -= k1.z * inv_n; f[7] -= k1.w * inv_n;
+    }
+  };
+  float amax = 0.f;
+#pragma unroll
+  for (int v = 0; v < MAXV; ++v) {
+    const int i = threadIdx.x + v * kQuantThreads;
+    if (i < nvec) {
+      const int r = i / vec_per_row, c = i % vec_per_row;
+      cache[v] = *reinterpret_cast<const uint4*>(src + 2 * ((int64_t)(r0 + r) * rs + 8 * c));
+      float f[8];
+      expand(cache[v], c, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) amax = fmaxf(amax, fabsf(f[u]));
     }
   }
 #pragma unroll
@@ -542,7 +569,7 @@ __global__ void __launch_bounds__(256) quantize_e4m3_kernel(const QuantArgs a) {
   __syncthreads();
   amax = red[0];
 #pragma unroll
-  for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i]);
+  for (int i = 1; i < 32; ++i) amax = fmaxf(amax, red[i]);
   const float scale = fmaxf(amax, 1e-12f) / 448.f;
   const float inv = 1.f / scale;
   if (threadIdx.x == 0) {
@@ -550,24 +577,99 @@ __global__ void __launch_bounds__(256) quantize_e4m3_kernel(const QuantArgs a) {
     if (which == 2) atomicMax(reinterpret_cast<unsigned int*>(a.vref + (int64_t)b * H + h), __float_as_uint(scale));
   }
   uint8_t* dst = a.dst[which] + (((int64_t)b * H + h) * N + r0) * dpad;
-  const int ovec_per_row = dpad / 8;  // 8 output bytes per step
-  for (int i = threadIdx.x; i < rows * ovec_per_row; i += 256) {
-    const int r = i / ovec_per_row, c = i % ovec_per_row;
-    uint2 o = make_uint2(0u, 0u);
-    if (8 * c < D) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + 2 * ((int64_t)(r0 + r) * rs + 8 * c));
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      float f[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (BF16) { f[2 * u] = __uint_as_float(w[u] << 16); f[2 * u + 1] = __uint_as_float(w[u] & 0xffff0000u); }
-        else { const __half2 hh = *reinterpret_cast<const __half2*>(&w[u]); f[2 * u] = __low2float(hh); f[2 * u + 1] = __high2float(hh); }
-      }
+  for (int v = 0; v < MAXV; ++v) {
+    const int i = threadIdx.x + v * kQuantThreads;
+    if (i < nvec) {
+      const int r = i / vec_per_row, c = i % vec_per_row;
+      float f[8];
+      expand(cache[v], c, f);
+      uint2 o;
       o.x = pack_e4m3x4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
       o.y = pack_e4m3x4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
+      *reinterpret_cast<uint2*>(dst + (int64_t)r * dpad + 8 * c) = o;
     }
-    *reinterpret_cast<uint2*>(dst + (int64_t)r * dpad + 8 * c) = o;
   }
+  if (dpad > D) {  // zero the padding bytes [D, dpad) (dpad - D is 0 or 8)
+    for (int r = threadIdx.x; r < rows; r += kQuantThreads)
+      *reinterpret_cast<uint2*>(dst + (int64_t)r * dpad + D) = make_uint2(0u, 0u);
+  }
+}
+
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (BF16) { f[2 * u] = __uint_as_float(w[u] << 16); f[2 * u + 1] = __uint_as_float(w[u] & 0xffff0000u); }
+    else { const __half2 hh = *reinterpret_cast<const __half2*>(&w[u]); f[2 * u] = __low2float(hh); f[2 * u + 1] = __high2float(hh); }
+  }
+}
+
+// column sums of K over a chunk of rows: warp w takes rows r0+w, r0+w+8, ...; lane l the 8 channels
+// [256 j + 8 l, +8) (16-byte loads); warps are combined through shared memory, chunks through atomics.
+template <bool BF16>
+__global__ void __launch_bounds__(256) k_colsum_kernel(const void* __restrict__ k, float* __restrict__ ksum, int64_t s0,
+                                                       int64_t s1, int64_t s2, int H, int N, int D, int rows_per_block) {
+  __shared__ float part[8][256];
+  const int nchunk = (N + rows_per_block - 1) / rows_per_block;
+  const int chunk = blockIdx.x % nchunk;
+  const int h = (blockIdx.x / nchunk) % H;
+  const int b = blockIdx.x / (nchunk * H);
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(k) + 2 * ((int64_t)b * s0 + (int64_t)h * s1);
+  const int r0 = chunk * rows_per_block;
+  const int r1 = (r0 + rows_per_block) < N ? (r0 + rows_per_block) : N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int d0 = 0; d0 < D; d0 += 256) {
+    const int d = d0 + 8 * lane;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (d < D) {
+#pragma unroll 4
+      for (int r = r0 + warp; r < r1; r += 8) {
+        float f[8];
+        unpack8<BF16>(*reinterpret_cast<const uint4*>(src + 2 * ((int64_t)r * s2 + d)), f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += f[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) part[warp][8 * lane + u] = acc[u];
+    __syncthreads();
+    const int dd = d0 + threadIdx.x;
+    if (dd < D) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+      atomicAdd(ksum + ((int64_t)b * H + h) * D + dd, t);
+    }
+    __syncthreads();
+  }
+}
+
+// qkm[b, h, q] = q . mean_seq(K) : one warp per query row, 16-byte loads
+template <bool BF16>
+__global__ void __launch_bounds__(256) q_dot_kmean_kernel(const void* __restrict__ q, const float* __restrict__ ksum,
+                                                          float* __restrict__ qkm, int64_t s0, int64_t s1, int64_t s2,
+                                                          int B, int Hq, int Hkv, int Nq, int Nkv, int D) {
+  const int64_t rowid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (rowid >= (int64_t)B * Hq * Nq) return;
+  const int lane = threadIdx.x & 31;
+  const int n = (int)(rowid % Nq);
+  const int h = (int)((rowid / Nq) % Hq);
+  const int b = (int)(rowid / ((int64_t)Nq * Hq));
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(q) + 2 * ((int64_t)b * s0 + (int64_t)h * s1 + (int64_t)n * s2);
+  const float* km = ksum + ((int64_t)b * Hkv + h / (Hq / Hkv)) * D;
+  float acc = 0.f;
+  for (int d = lane * 8; d < D; d += 256) {
+    float f[8];
+    unpack8<BF16>(*reinterpret_cast<const uint4*>(src + 2 * d), f);
+    const float4 k0 = *reinterpret_cast<const float4*>(km + d), k1 = *reinterpret_cast<const float4*>(km + d + 4);
+    acc = fmaf(f[0], k0.x, acc); acc = fmaf(f[1], k0.y, acc); acc = fmaf(f[2], k0.z, acc); acc = fmaf(f[3], k0.w, acc);
+    acc = fmaf(f[4], k1.x, acc); acc = fmaf(f[5], k1.y, acc); acc = fmaf(f[6], k1.z, acc); acc = fmaf(f[7], k1.w, acc);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) qkm[rowid] = acc / (float)Nkv;
 }
 
 template <int NB, bool OUT_BF16>

@@ -21,13 +21,15 @@ def _mk(B, Hq, Hkv, Nq, Nkv, D, dtype, amp=0.5, seed=0):
   return q, k, v
 
 
-def _fp8(q, k, v, **kw):
+def _fp8(q, k, v, smooth_k=True, **kw):
   import ffpa_attn
 
   n0 = ffpa_attn._C.launch_count()
-  out = ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=ffpa_attn.CUDABackend(enable_fp8=True), **kw)
+  be = ffpa_attn.CUDABackend(enable_fp8=True, fp8_smooth_k=smooth_k)
+  out = ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=be, **kw)
   torch.cuda.synchronize()
-  assert ffpa_attn._C.launch_count() - n0 == 2, "expected quantise + attention launches"
+  # quantise + attention (+ K column sums + q.mean for smooth-K)
+  assert ffpa_attn._C.launch_count() - n0 == (4 if smooth_k else 2)
   return out
 
 
@@ -87,6 +89,33 @@ def test_fp8_lse_small_amplitude():
   finally:
     ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.AUTO)
   _, lref = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu())
+  assert np.abs(lse.cpu().numpy() - lref).max() < 5e-2
+
+
+def test_fp8_smooth_k_handles_large_key_mean_and_corrects_lse():
+  """smooth-K (reference default, functional.py:246; cute/fp8/smooth_k.cuh:61-137): a large per-channel mean of K
+  wastes the e4m3 range; subtracting mean_seq(K) leaves softmax/O unchanged and the LSE is shifted back by
+  scale * q . mean (tests/test_ffpa_fp8.py:238-251: LSE atol 5e-2)."""
+  import ffpa_attn
+  import ffpa_attn.cuda as fc
+
+  torch.manual_seed(5)
+  B, H, N, D = 1, 2, 512, 256
+  q = (torch.randn(B, H, N, D) * 0.5).to(torch.bfloat16).to(DEV)
+  k = (torch.randn(B, H, N, D) * 0.5 + 3.0 * torch.randn(1, H, 1, D)).to(torch.bfloat16).to(DEV)
+  v = (torch.randn(B, H, N, D) * 0.5).to(torch.bfloat16).to(DEV)
+  ref, lref = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu())
+  err_on = np.abs(_fp8(q, k, v, smooth_k=True).float().cpu().numpy() - ref).max()
+  err_off = np.abs(_fp8(q, k, v, smooth_k=False).float().cpu().numpy() - ref).max()
+  assert err_on < 4e-2, err_on
+  assert err_on < err_off, (err_on, err_off)
+  ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.CUTE_TMA_FP8)
+  try:
+    _, lse = torch.ops.ffpa_attn._fwd_cuda(q, k, v, q.new_empty(0), 0, 1, 0, D ** -0.5, 0.0, 0, 0, True, False,
+                                           0, 0, 0, 0, 0, False, 256, False, 256)
+    torch.cuda.synchronize()
+  finally:
+    ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.AUTO)
   assert np.abs(lse.cpu().numpy() - lref).max() < 5e-2
 
 
