@@ -308,11 +308,9 @@ def main():
     n_e2e = max(3, min(args.steps, 10))
 
     def e2e_step():
-      dq_ = hq.to(dev, non_blocking=True)
-      dk_ = hk.to(dev, non_blocking=True)
-      dv_ = hv.to(dev, non_blocking=True)
-      o = ffpa_attn.ffpa_attn_func(dq_, dk_, dv_, **kw)
-      ho.copy_(o, non_blocking=True)
+      # public host-buffer call: head-chunked copy-in / kernel / copy-out pipeline, result complete
+      # in `ho` (host) when it returns
+      ffpa_attn.ffpa_attn_host_func(hq, hk, hv, out=ho, **kw)
 
     for _ in range(2):
       e2e_step()

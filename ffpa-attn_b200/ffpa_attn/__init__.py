@@ -6,10 +6,12 @@ Importing this package loads ``libffpa_b200.so`` (hand-written sm_100a kernels b
 from .cuda import CudaBackendImpl, get_cuda_backend_impl, set_cuda_backend_impl
 from .ffpa_attn_interface import ffpa_attn_func, ffpa_attn_varlen_func
 from .functional import CUDABackend, FFPAAttnFunc, FFPAAttnMeta
+from .host import ffpa_attn_host_func
 
 __all__ = [
   "ffpa_attn_func",
   "ffpa_attn_varlen_func",
+  "ffpa_attn_host_func",
   "CUDABackend",
   "FFPAAttnFunc",
   "FFPAAttnMeta",

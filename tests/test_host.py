@@ -170,6 +170,27 @@ def test_cpu_tensors_fail_loudly_no_fallback():
     ffpa_attn_func(q, k, v)
 
 
+def test_host_func_units_partition_kv_heads_and_no_cpu_fallback():
+  from ffpa_attn import ffpa_attn_host_func
+  from ffpa_attn.host import _units
+
+  for B, Hkv, chunks in [(1, 32, 8), (2, 8, 3), (3, 1, 8), (1, 5, 16)]:
+    units = _units(B, Hkv, chunks)
+    for b in range(B):
+      mine = [(lo, hi) for (bb, lo, hi) in units if bb == b]
+      assert mine[0][0] == 0 and mine[-1][1] == Hkv
+      assert all(a[1] == c[0] and a[0] < a[1] for a, c in zip(mine, mine[1:]))
+      assert len(mine) == min(Hkv, chunks)
+  q, k, v = _qkv()
+  if not torch.cuda.is_available():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+      ffpa_attn_host_func(q, k, v)
+  with pytest.raises(NotImplementedError):
+    ffpa_attn_host_func(q, k, v, dropout_p=0.1)
+  with pytest.raises(ValueError, match="enable_gqa"):
+    ffpa_attn_host_func(q, k[:, :1], v[:, :1])
+
+
 def test_backend_kwarg_accepts_only_cuda():
   from ffpa_attn import CUDABackend, FFPAAttnMeta
 

@@ -69,3 +69,26 @@ def test_varlen_validation_errors():
   bad[-1] += 1
   with pytest.raises(ValueError):
     ffpa_attn.ffpa_attn_varlen_func(q, k, v, bad, ck, 64, 64)
+
+
+@pytest.mark.parametrize("causal,Hkv,chunks", [(False, 4, 8), (True, 2, 2), (False, 4, 3)])
+def test_host_buffer_entry_matches_device_call_and_oracle(causal, Hkv, chunks):
+  """ffpa_attn_host_func: pinned host q/k/v in, pinned host output back; head-chunked pipeline must be
+  bit-identical to the one-shot device call (same kernel, same per-head arithmetic)."""
+  import ffpa_attn
+
+  torch.manual_seed(3)
+  B, Hq, N, D = 2, 4, 384, 256
+  hq = torch.randn(B, Hq, N, D).to(torch.bfloat16).pin_memory()
+  hk = torch.randn(B, Hkv, N, D).to(torch.bfloat16).pin_memory()
+  hv = torch.randn(B, Hkv, N, D).to(torch.bfloat16).pin_memory()
+  ho = torch.zeros(B, Hq, N, D, dtype=torch.bfloat16).pin_memory()
+  ret = ffpa_attn.ffpa_attn_host_func(hq, hk, hv, out=ho, is_causal=causal, enable_gqa=Hq != Hkv, chunks=chunks)
+  assert ret is ho
+  dense = ffpa_attn.ffpa_attn_func(hq.to(DEV), hk.to(DEV), hv.to(DEV), is_causal=causal, enable_gqa=Hq != Hkv)
+  assert torch.equal(dense.cpu(), ho)
+  ref, _ = orc.attention_fwd(hq, hk, hv, causal=causal)
+  assert np.abs(ho.float().numpy() - ref).max() < 1e-2
+  # pageable inputs and an allocated output also work
+  out2 = ffpa_attn.ffpa_attn_host_func(hq.clone(), hk.clone(), hv.clone(), is_causal=causal, enable_gqa=Hq != Hkv)
+  assert torch.equal(out2, ho)
