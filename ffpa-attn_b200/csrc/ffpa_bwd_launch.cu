@@ -70,7 +70,10 @@ __global__ void f32_to_16_kernel(const float* __restrict__ src, void* __restrict
 }
 
 int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
-  const int D = a.head_dim, nqk = (D + 63) / 64;
+  const int D = a.head_dim;
+  // head_dim > 512: two output-slab passes per item; box count rounded up to even (TMA zero-fills)
+  const int nqk = D > 512 ? (D + 127) / 128 * 2 : (D + 63) / 64;
+  const int n_pass = D > 512 ? 2 : 1;
   const int nq_pad = (a.seqlen_q + 127) / 128 * 128;
   const uint64_t need = align256(2ull * a.batch * a.heads_q * nq_pad * sizeof(float));  // lse2 + delta (split buffers optional)
   if (!a.workspace || a.workspace_bytes < need)
@@ -85,10 +88,13 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
 
   CUtensorMap q_km, q_mn, k_km, k_mn, v_km, do_km, do_mn;
   const int B = a.batch, Hq = a.heads_q, Hkv = a.heads_kv, Nq = a.seqlen_q, Nkv = a.seqlen_kv;
-  if (!make_map4(&q_km, a.q, a.q_stride, B, Hq, Nq, D, 64, 64) || !make_map4(&q_mn, a.q, a.q_stride, B, Hq, Nq, D, 64, 128) ||
-      !make_map4(&k_km, a.k, a.k_stride, B, Hkv, Nkv, D, 64, 64) || !make_map4(&k_mn, a.k, a.k_stride, B, Hkv, Nkv, D, 64, 128) ||
-      !make_map4(&v_km, a.v, a.v_stride, B, Hkv, Nkv, D, 64, 64) ||
-      !make_map4(&do_km, a.d_o, a.do_stride, B, Hq, Nq, D, 64, 64) || !make_map4(&do_mn, a.d_o, a.do_stride, B, Hq, Nq, D, 64, 128))
+  // packed variable-length mode: [total tokens, H, D] operands (map batch extent 1); Nq / Nkv are the maxima
+  const bool varlen = a.cu_seqlens_q != nullptr;
+  const int mb = varlen ? 1 : B, mq = varlen ? a.total_q : Nq, mk = varlen ? a.total_k : Nkv;
+  if (!make_map4(&q_km, a.q, a.q_stride, mb, Hq, mq, D, 64, 64) || !make_map4(&q_mn, a.q, a.q_stride, mb, Hq, mq, D, 64, 128) ||
+      !make_map4(&k_km, a.k, a.k_stride, mb, Hkv, mk, D, 64, 64) || !make_map4(&k_mn, a.k, a.k_stride, mb, Hkv, mk, D, 64, 128) ||
+      !make_map4(&v_km, a.v, a.v_stride, mb, Hkv, mk, D, 64, 64) ||
+      !make_map4(&do_km, a.d_o, a.do_stride, mb, Hq, mq, D, 64, 64) || !make_map4(&do_mn, a.d_o, a.do_stride, mb, Hq, mq, D, 64, 128))
     return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed in backward");
 
   // optional fp32 accumulation buffers for chunked dK / dV items
@@ -97,7 +103,7 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   {
     const uint64_t base = align256(2ull * a.batch * a.heads_q * nq_pad * sizeof(float));
     const uint64_t one = align256((uint64_t)a.batch * a.heads_kv * a.seqlen_kv * D * sizeof(float));
-    if (may_split_kv(a.batch, a.heads_kv, a.seqlen_kv) && a.workspace_bytes >= base + 2 * one) {
+    if (!varlen && may_split_kv(a.batch, a.heads_kv, a.seqlen_kv) && a.workspace_bytes >= base + 2 * one) {
       dk32 = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + base);
       dv32 = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + base + one);
     }
@@ -112,6 +118,9 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   for (int i = 0; i < 4; ++i) kp.bias_stride[i] = a.bias_stride[i];
   kp.dropout_p = a.dropout_p; kp.philox_seed = a.philox_seed; kp.philox_offset = a.philox_offset;
   kp.dbias = a.d_bias;
+  kp.cu_q = a.cu_seqlens_q;
+  kp.cu_k = a.cu_seqlens_k;
+  kp.total_q = a.total_q; kp.total_k = a.total_k;
   const int max_clusters = sm_count() / 2;
   const int off = Nkv - Nq;
   auto run = [&](int kind, void* out, const int64_t* ostride, int rows, int heads, float* acc32,
@@ -143,7 +152,7 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
       tsum += t;
     }
     const long long nbh = (long long)B * heads;
-    const double avg = (double)tsum * nbh / max_clusters;  // tiles per cluster if perfectly balanced
+    const double avg = (double)tsum * nbh * n_pass / max_clusters;  // tiles per cluster if perfectly balanced
     kp.n_chunks = 1;
     kp.chunk_len = tmax;
     kp.out32 = nullptr;
@@ -158,11 +167,12 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
         if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
       }
     }
-    kp.n_items = kp.n_rtiles * kp.n_chunks * (int)nbh;
+    kp.n_pass = n_pass;
+    kp.n_items = kp.n_rtiles * kp.n_chunks * (int)nbh * n_pass;
     const int ncl = kp.n_items < max_clusters ? kp.n_items : max_clusters;
     kp.sched = nullptr;
     kp.sched_stride = 0;
-    if ((a.causal || kp.n_chunks > 1) && kp.n_items > ncl) {
+    if ((a.causal || kp.n_chunks > 1) && kp.n_items > ncl && !varlen) {
       std::vector<int> cost((size_t)kp.n_items);
       for (int it = 0; it < kp.n_items; ++it) {
         const int rt = it % kp.n_rtiles;

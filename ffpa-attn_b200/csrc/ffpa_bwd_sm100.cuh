@@ -15,6 +15,10 @@
 //   kind dK: rows = keys,    cols = queries A1=K  B1=Q  A2=V  B2=dO T=dS^T  B3=Q
 //   kind dV: rows = keys,    cols = queries A1=K  B1=Q              T=P^T   B3=dO
 // TMEM (D=512): ACC 256 columns (lane folded, 4 N=128 slices), S 2x64, dP 2x64 = 512.
+// head_dim in (512, 1024] (LARGE): the accumulator no longer fits next to S / dP, so every item runs
+// as two slab passes (each pass = one virtual work item owning half of the output columns and
+// recomputing S / dP), and only A1 stays resident in SMEM: A2 is streamed through the ring next to
+// B2, one 64-wide head-dim box of each per stage ("Split-D" in its pure form: O(1) SMEM in D).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -41,12 +45,17 @@ struct BwdCfg {
   static constexpr bool HAS_DP = (KIND != kKindDV);
   static constexpr int HD = NQK * 64;
   static constexpr int DVP = ((HD + 127) / 128) * 128;
-  static constexpr int NSL = DVP / 128;                    // N=128 slices of the accumulator
-  static constexpr int ACC_COLS = DVP / 2;
+  static constexpr bool LARGE = NQK > 8;                   // head_dim > 512: slab passes + streamed A2
+  static constexpr int NPASS = LARGE ? 2 : 1;
+  static constexpr int SLAB = LARGE ? ((DVP / 2 + 127) / 128) * 128 : DVP;  // output columns per pass
+  static constexpr int NSL = SLAB / 128;                   // N=128 slices of the accumulator
+  static constexpr int ACC_COLS = SLAB / 2;
   static constexpr int KST = (NQK + 1) / 2;                // 16 KB K-major stages per streamed tile and operand
   static constexpr int S_BASE = 256, DP_BASE = 384;
   static constexpr int A_BYTES = NQK * 8192;
-  static constexpr int NA = HAS_DP ? 2 : 1;
+  static constexpr int NA = (HAS_DP && !LARGE) ? 2 : 1;    // resident operands
+  // ring stages one step consumes before the B3 slices (keeps N=256 stage pairs on even indices)
+  static constexpr int PRE = KST + (HAS_DP ? (LARGE ? NQK : KST) : 0);
   static constexpr int T_BYTES = 2 * 16384;
   static constexpr int kBudget = kSmemLimit - 3072;
   static constexpr int kRaw = (kBudget - NA * A_BYTES - T_BYTES) / 16384;
@@ -56,8 +65,9 @@ struct BwdCfg {
   // WIDE: accumulate with N=256 MMAs (a slice = two consecutive ring stages): T is re-read from SMEM 2x
   // instead of 4x per tile. With N=128 everywhere the operand fetch needs 125 B/clk of the 128 B/clk SMEM
   // port (A 2 KB + B 2 KB per 32-cycle MMA), which is what limits these kernels.
-  static constexpr bool WIDE = (NSL % 2 == 0) && (NST % 2 == 0) && (HAS_DP || KST % 2 == 0);
-  static_assert(ACC_COLS <= 256, "backward kernels support head_dim <= 512");
+  static constexpr bool WIDE = (NSL % 2 == 0) && (NST % 2 == 0) && (PRE % 2 == 0);
+  static_assert(!LARGE || NQK % 2 == 0, "head_dim > 512 is rounded up to a multiple of 128");
+  static_assert(ACC_COLS <= 256, "backward kernels support head_dim <= 1024");
 };
 
 struct Barriers {
@@ -87,19 +97,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr) {
 struct TileRange { int first, count; };
 
 template <int KIND>
-__device__ __forceinline__ TileRange col_tiles(const BwdKernelParams& p, int r0) {
+__device__ __forceinline__ TileRange col_tiles(int causal, int nq, int nkv, int r0) {
   if (KIND == kKindDQ) {  // rows = queries starting at r0; columns = KV tiles
-    int tc = (p.seqlen_kv + 127) >> 7;
-    if (p.causal) {
-      int lim = ((r0 + 127 + (p.seqlen_kv - p.seqlen_q)) >> 7) + 1;
+    int tc = (nkv + 127) >> 7;
+    if (causal) {
+      int lim = ((r0 + 127 + (nkv - nq)) >> 7) + 1;
       tc = lim < tc ? lim : tc;
     }
     return {0, tc < 1 ? 1 : tc};
   } else {  // rows = keys starting at r0; columns = query tiles (per head of the group)
-    const int tq = (p.seqlen_q + 127) >> 7;
+    const int tq = (nq + 127) >> 7;
     int first = 0;
-    if (p.causal) {
-      const int qmin = r0 - (p.seqlen_kv - p.seqlen_q);  // first query row that sees key r0
+    if (causal) {
+      const int qmin = r0 - (nkv - nq);  // first query row that sees key r0
       first = qmin > 0 ? (qmin >> 7) : 0;
       if (first > tq) first = tq;
     }
@@ -110,7 +120,9 @@ __device__ __forceinline__ TileRange col_tiles(const BwdKernelParams& p, int r0)
 // One work item = 128 stationary rows x a contiguous chunk of the streamed (head, column-tile)
 // sequence. With n_chunks > 1 (few, long items: e.g. GQA + causal dK/dV) partial accumulators are
 // added into an fp32 buffer with atomics and converted afterwards.
-struct Item { int rt, bh, s0, n; TileRange tr; };
+// Packed variable-length mode (p.cu_q != nullptr): the item carries the lengths and token offsets of its
+// sequence; row tiles past the end of a short sequence are empty items (n = 0, nothing stored).
+struct Item { int rt, bh, s0, n, pass; TileRange tr; int nq, nkv, qoff, koff, bt; };
 
 template <int KIND>
 __device__ __forceinline__ Item decode_item(const BwdKernelParams& p, int item, int n_inner) {
@@ -118,8 +130,22 @@ __device__ __forceinline__ Item decode_item(const BwdKernelParams& p, int item, 
   it.rt = item % p.n_rtiles;
   const int rest = item / p.n_rtiles;
   const int chunk = rest % p.n_chunks;
-  it.bh = rest / p.n_chunks;
-  it.tr = col_tiles<KIND>(p, it.rt * 128);
+  const int rest2 = rest / p.n_chunks;
+  it.pass = rest2 % p.n_pass;   // output-column slab (head_dim > 512); adjacent in the item order
+  it.bh = rest2 / p.n_pass;
+  const int b = it.bh / ((KIND == kKindDQ) ? p.heads_q : p.heads_kv);
+  if (p.cu_q != nullptr) {
+    // offsets are clamped to the packed extents so a malformed cu_seqlens can never address past the tensors
+    it.qoff = min(max(__ldg(p.cu_q + b), 0), p.total_q);
+    it.nq = max(min(__ldg(p.cu_q + b + 1), p.total_q) - it.qoff, 0);
+    it.koff = min(max(__ldg(p.cu_k + b), 0), p.total_k);
+    it.nkv = max(min(__ldg(p.cu_k + b + 1), p.total_k) - it.koff, 0);
+    it.bt = 0;
+    if (it.rt * 128 >= ((KIND == kKindDQ) ? it.nq : it.nkv)) { it.tr = {0, 0}; it.s0 = 0; it.n = 0; return it; }
+  } else {
+    it.nq = p.seqlen_q; it.nkv = p.seqlen_kv; it.qoff = 0; it.koff = 0; it.bt = b;
+  }
+  it.tr = col_tiles<KIND>(p.causal, it.nq, it.nkv, it.rt * 128);
   const int tfull = it.tr.count * n_inner;
   if (p.n_chunks == 1) { it.s0 = 0; it.n = tfull; }
   else {
@@ -210,7 +236,19 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           ++rc;
         }
       };
-      auto load_mnmajor = [&](const CUtensorMap* m, int c_row0, int hh, int bb) {
+      // LARGE: one stage = [A2 box | B2 box] of the same 64-wide head-dim box (64 rows of this CTA each)
+      auto load_pair = [&](const CUtensorMap* ma, int a_row0, int ha_, const CUtensorMap* mb, int c_row0, int hh, int bb) {
+        for (int jb = 0; jb < NQK; ++jb) {
+          const uint32_t stage = rc % Cfg::NST, n = rc / Cfg::NST;
+          ptx::mbar_wait(bar(bars.r_empty[stage]), (n & 1) ^ 1);
+          if (rank == 0) ptx::mbar_expect_tx(bar(bars.r_full[stage]), 2 * 16384);
+          const uint32_t l_full = ptx::mapa(bar(bars.r_full[stage]), 0);
+          ptx::tma_load_4d_2sm(sR + stage * 16384, ma, l_full, jb * 64, a_row0 + 64 * (int)rank, ha_, bb);
+          ptx::tma_load_4d_2sm(sR + stage * 16384 + 8192, mb, l_full, jb * 64, c_row0 + 64 * (int)rank, hh, bb);
+          ++rc;
+        }
+      };
+      auto load_mnmajor = [&](const CUtensorMap* m, int c_row0, int hh, int bb, int d_base) {
         // NSL stages of [128 rows x 64 d(this CTA's half of the 128-wide slice)]
 #pragma unroll
         for (int s = 0; s < Cfg::NSL; ++s) {
@@ -220,7 +258,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           const uint32_t l_full = ptx::mapa(bar(bars.r_full[stage]), 0);
           // WIDE: stage pair (s & ~1, s | 1) = N=256 slice s/2, this CTA's 128 columns as two 64-wide boxes
           const int dcol = Cfg::WIDE ? 256 * (s >> 1) + 128 * (int)rank + 64 * (s & 1) : 128 * s + 64 * (int)rank;
-          ptx::tma_load_4d_2sm(sR + stage * 16384, m, l_full, dcol, c_row0, hh, bb);
+          ptx::tma_load_4d_2sm(sR + stage * 16384, m, l_full, d_base + dcol, c_row0, hh, bb);
           ++rc;
         }
       };
@@ -229,8 +267,10 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         if (item_s < 0) break;
         const Item itm = decode_item<KIND>(p, item_s, n_inner);
         const int bh = itm.bh;
-        const int hs = bh % heads_it, b = bh / heads_it;  // head of the stationary operand
-        const int r0 = itm.rt * 128;
+        const int hs = bh % heads_it, b = itm.bt;  // head of the stationary operand; batch coordinate of the maps
+        // token rows of the stationary (r0) and streamed (c_off + tile * 128) operands
+        const int r0 = ((KIND == kKindDQ) ? itm.qoff : itm.koff) + itm.rt * 128;
+        const int c_off = (KIND == kKindDQ) ? itm.koff : itm.qoff;
         const TileRange tr = itm.tr;
         const int T = itm.n;
         if (T <= 0) continue;
@@ -241,21 +281,24 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
 #pragma unroll
         for (int jb = 0; jb < NQK; ++jb) {
           ptx::tma_load_4d_2sm(sA1 + jb * 8192, &map_a1, l_a_full, jb * 64, r0 + 64 * (int)rank, ha, b);
-          if (HAS_DP) ptx::tma_load_4d_2sm(sA2 + jb * 8192, &map_a2, l_a_full, jb * 64, r0 + 64 * (int)rank, ha, b);
+          if (Cfg::NA == 2) ptx::tma_load_4d_2sm(sA2 + jb * 8192, &map_a2, l_a_full, jb * 64, r0 + 64 * (int)rank, ha, b);
         }
         for (int step = 0; step <= T; ++step) {
           if (step < T) {
             const int sa = itm.s0 + step;
             const int gi = sa / tr.count, ci = tr.first + sa % tr.count;
             const int hb = (KIND == kKindDQ) ? hs / group : hs * group + gi;  // head of the streamed operands
-            load_kmajor(&map_b1, ci * 128, hb, b);
-            if (HAS_DP) load_kmajor(&map_b2, ci * 128, hb, b);
+            load_kmajor(&map_b1, c_off + ci * 128, hb, b);
+            if (HAS_DP) {
+              if constexpr (Cfg::LARGE) load_pair(&map_a2, r0, ha, &map_b2, c_off + ci * 128, hb, b);
+              else load_kmajor(&map_b2, c_off + ci * 128, hb, b);
+            }
           }
           if (step >= 1) {
             const int st = itm.s0 + step - 1;
             const int gi = st / tr.count, ci = tr.first + st % tr.count;
             const int hb = (KIND == kKindDQ) ? hs / group : hs * group + gi;
-            load_mnmajor(&map_b3, ci * 128, hb, b);
+            load_mnmajor(&map_b3, c_off + ci * 128, hb, b, itm.pass * Cfg::SLAB);
           }
         }
         ++it;
@@ -288,6 +331,21 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           ++rc;
         }
       };
+      auto gemm_pair = [&](uint32_t d_tmem) {  // LARGE: A2 and B2 boxes streamed side by side
+        for (int jb = 0; jb < NQK; ++jb) {
+          const uint32_t stage = rc % Cfg::NST, n = rc / Cfg::NST;
+          ptx::mbar_wait(bar(bars.r_full[stage]), n & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t ad = ptx::make_smem_desc_sw128(sR + stage * 16384 + k4 * 32, 16, 1024);
+            const uint64_t bd = ptx::make_smem_desc_sw128(sR + stage * 16384 + 8192 + k4 * 32, 16, 1024);
+            ptx::umma_f16_ss<CG>(d_tmem, ad, bd, idesc_s, (jb | k4) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit_mc<CG>(bar(bars.r_empty[stage]), 0x3);
+          ++rc;
+        }
+      };
       for (uint32_t kidx = 0;; ++kidx) {
         const int item_s = next_item(p, cluster, nclusters, kidx);
         if (item_s < 0) break;
@@ -300,7 +358,10 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           if (step < T) {
             const uint32_t sbuf = g & 1;
             gemm_kmajor(sA1, tmem + Cfg::S_BASE + 64 * sbuf);
-            if (HAS_DP) gemm_kmajor(sA2, tmem + Cfg::DP_BASE + 64 * sbuf);
+            if (HAS_DP) {
+              if constexpr (Cfg::LARGE) gemm_pair(tmem + Cfg::DP_BASE + 64 * sbuf);
+              else gemm_kmajor(sA2, tmem + Cfg::DP_BASE + 64 * sbuf);
+            }
             ptx::umma_commit_mc<CG>(bar(bars.s_full[sbuf]), 0x3);
             if (step == T - 1) ptx::umma_commit_mc<CG>(bar(bars.a_empty), 0x3);
             ++g;
@@ -359,7 +420,6 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;
     const uint32_t l_t_full0 = ptx::mapa(bar(bars.t_full[0]), 0);
     const uint32_t l_t_full1 = ptx::mapa(bar(bars.t_full[1]), 0);
-    const int off = p.seqlen_kv - p.seqlen_q;
     uint32_t g = 0;
     for (uint32_t kidx = 0;; ++kidx) {
       const int item_s = next_item(p, cluster, nclusters, kidx);
@@ -370,13 +430,16 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       const int r0 = itm.rt * 128;
       const TileRange tr = itm.tr;
       const int T = itm.n;
-      const int grow = r0 + 64 * (int)rank + (int)row;  // global stationary row (query or key)
-      const bool row_ok = grow < ((KIND == kKindDQ) ? p.seqlen_q : p.seqlen_kv);
+      const int grow = r0 + 64 * (int)rank + (int)row;  // stationary row (query or key) inside its sequence
+      const int seq_q = itm.nq, seq_kv = itm.nkv;
+      const int off = seq_kv - seq_q;
+      const bool row_ok = grow < ((KIND == kKindDQ) ? seq_q : seq_kv);
+      const int tok0 = (KIND == kKindDQ) ? itm.qoff : itm.koff;  // token offset of the output rows (packed mode)
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
-                      2 * ((int64_t)b * p.out_stride[0] + (int64_t)hs * p.out_stride[1] + (int64_t)grow * p.out_stride[2]);
+                      2 * ((int64_t)itm.bt * p.out_stride[0] + (int64_t)hs * p.out_stride[1] + (int64_t)(tok0 + grow) * p.out_stride[2]);
       if (T <= 0) {
         // nothing contributes: gradient is zero (already so in the pre-zeroed fp32 buffer of split mode)
-        if (row_ok && p.out32 == nullptr) {
+        if (row_ok && p.out32 == nullptr && itm.pass == 0) {
           for (int d = (int)(kh * 2 + ch) * 8; d < p.head_dim; d += 32)
             *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(0, 0, 0, 0);
         }
@@ -415,7 +478,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         // visibility: key <= query + off (causal), key < Nkv; padded / empty query rows carry lse2=+inf
         int lim_lo = 0, lim_hi = 0x7fffffff;  // visible columns: lim_lo <= col <= lim_hi
         if (KIND == kKindDQ) {
-          lim_hi = p.seqlen_kv - 1;
+          lim_hi = seq_kv - 1;
           if (p.causal) { const int cl = grow + off; lim_hi = cl < lim_hi ? cl : lim_hi; }
         } else {
           if (p.causal) lim_lo = grow - off;
@@ -445,7 +508,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             float xs = fmaf(__uint_as_float(sr[jj]), p.scale_log2, -l2);
             float mult = 1.f;
             if constexpr (GENERAL) {
-              const bool inb = qi < p.seqlen_q && ki < p.seqlen_kv;
+              const bool inb = qi < seq_q && ki < seq_kv;
               if (p.bias_kind != 0 && inb) {
                 const int64_t bo = (int64_t)b * p.bias_stride[0] + (int64_t)hq_cur * p.bias_stride[1] +
                                    (int64_t)qi * p.bias_stride[2] + ki;
@@ -471,7 +534,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
               const float ds = pe * (__uint_as_float(dr[jj]) * mult - dl);
               e[u] = ds;
               if constexpr (GENERAL && KIND == kKindDQ) {
-                if (p.dbias != nullptr && qi < p.seqlen_q && ki < p.seqlen_kv)
+                if (p.dbias != nullptr && itm.pass == 0 && qi < seq_q && ki < seq_kv)
                   p.dbias[(((int64_t)b * p.heads_q + hq_cur) * p.seqlen_q + qi) * (int64_t)p.seqlen_kv + ki] = ds;
               }
             } else {
@@ -509,8 +572,9 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           ptx::tmem_wait_ld();
           // TMEM column 64 s + 32 ch + j of lane half kh: N=128 slices -> d = 128 s + 64 kh + 32 ch + j;
           // N=256 slices (WIDE) -> column c = 64 (s & 1) + 32 ch + j of slice s/2 -> d = 256 (s/2) + 128 kh + c
-          const int d0 = Cfg::WIDE ? 256 * (s >> 1) + 128 * (int)kh + 64 * (s & 1) + 32 * (int)ch
-                                   : 128 * s + 64 * (int)kh + 32 * (int)ch;
+          const int d0 = itm.pass * Cfg::SLAB +
+                         (Cfg::WIDE ? 256 * (s >> 1) + 128 * (int)kh + 64 * (s & 1) + 32 * (int)ch
+                                    : 128 * s + 64 * (int)kh + 32 * (int)ch);
           if (row_ok && p.out32 != nullptr) {
             // split mode: accumulate this chunk's partial result (fp32, [B, H, rows, D] contiguous)
             float* dst = p.out32 + (((int64_t)b * heads_it + hs) * p.out_rows + grow) * (int64_t)p.head_dim;
@@ -553,7 +617,7 @@ __global__ void bwd_preprocess_kernel(const void* __restrict__ o, const void* __
                                       const float* __restrict__ lse, float* __restrict__ lse2,
                                       float* __restrict__ delta, int64_t os0, int64_t os1, int64_t os2,
                                       int64_t ds0, int64_t ds1, int64_t ds2, int B, int H, int Nq,
-                                      int nq_pad, int D) {
+                                      int nq_pad, int D, const int* __restrict__ cu_q, int total_q) {
   const int warps_per_block = blockDim.x >> 5;
   const int64_t rowid = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int64_t total = (int64_t)B * H * nq_pad;
@@ -562,12 +626,19 @@ __global__ void bwd_preprocess_kernel(const void* __restrict__ o, const void* __
   const int q = (int)(rowid % nq_pad);
   const int64_t bh = rowid / nq_pad;
   const int h = (int)(bh % H), b = (int)(bh / H);
+  // packed mode: sequence b owns tokens [cu_q[b], cu_q[b+1]); LSE is [H, total_q]
+  int64_t tok = q, bt = b, lse_idx = bh * Nq + q;
+  if (cu_q != nullptr) {
+    const int q0 = min(max(__ldg(cu_q + b), 0), total_q);
+    Nq = min(__ldg(cu_q + b + 1), total_q) - q0;
+    tok = (int64_t)q0 + q; bt = 0; lse_idx = (int64_t)h * total_q + tok;
+  }
   if (q >= Nq) {
     if (lane == 0) { lse2[rowid] = INFINITY; delta[rowid] = 0.f; }
     return;
   }
-  const uint8_t* po = reinterpret_cast<const uint8_t*>(o) + 2 * (b * os0 + h * os1 + q * os2);
-  const uint8_t* pd = reinterpret_cast<const uint8_t*>(d_o) + 2 * (b * ds0 + h * ds1 + q * ds2);
+  const uint8_t* po = reinterpret_cast<const uint8_t*>(o) + 2 * (bt * os0 + h * os1 + tok * os2);
+  const uint8_t* pd = reinterpret_cast<const uint8_t*>(d_o) + 2 * (bt * ds0 + h * ds1 + tok * ds2);
   float acc = 0.f;
   for (int d = lane * 8; d < D; d += 256) {
     const uint4 a = *reinterpret_cast<const uint4*>(po + 2 * d);
@@ -591,7 +662,7 @@ __global__ void bwd_preprocess_kernel(const void* __restrict__ o, const void* __
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
   if (lane == 0) {
-    const float l = lse[bh * Nq + q];
+    const float l = lse[lse_idx];
     lse2[rowid] = (l == -INFINITY) ? INFINITY : l * 1.4426950408889634f;
     delta[rowid] = acc;
   }
@@ -634,7 +705,12 @@ static int dispatch_bwd_nqk(int nqk, const CUtensorMap& a1, const CUtensorMap& a
     case 6: return launch_bwd_variant<6, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
     case 7: return launch_bwd_variant<7, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
     case 8: return launch_bwd_variant<8, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    default: return set_error(FFPA_ERR_UNSUPPORTED, "backward supports head_dim <= 512");
+    // head_dim > 512: the launcher rounds the box count up to an even number (TMA zero fill)
+    case 10: return launch_bwd_variant<10, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 12: return launch_bwd_variant<12, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 14: return launch_bwd_variant<14, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 16: return launch_bwd_variant<16, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    default: return set_error(FFPA_ERR_UNSUPPORTED, "backward supports head_dim <= 1024");
   }
 }
 
@@ -661,7 +737,7 @@ int launch_preprocess(const ffpa_bwd_params& a, float* lse2, float* delta, int n
   const int64_t blocks = (rows + wpb - 1) / wpb;
   bwd_preprocess_kernel<BF16><<<dim3((unsigned)blocks), dim3(wpb * 32), 0, stream>>>(
       a.o, a.d_o, a.lse, lse2, delta, a.o_stride[0], a.o_stride[1], a.o_stride[2], a.do_stride[0],
-      a.do_stride[1], a.do_stride[2], a.batch, a.heads_q, a.seqlen_q, nq_pad, a.head_dim);
+      a.do_stride[1], a.do_stride[2], a.batch, a.heads_q, a.seqlen_q, nq_pad, a.head_dim, a.cu_seqlens_q, a.total_q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "backward preprocess launch failed: %s", cudaGetErrorString(e));
   count_launch();

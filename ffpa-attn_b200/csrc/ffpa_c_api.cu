@@ -141,7 +141,14 @@ int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream) {
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "Q heads (%d) must be an integer multiple of KV heads (%d)", p->heads_q, p->heads_kv);
   if (p->head_dim % 8 != 0) return set_error(FFPA_ERR_INVALID_ARGUMENT, "head_dim must be a multiple of 8, got %d", p->head_dim);
   if (p->head_dim > 1024) return set_error(FFPA_ERR_INVALID_ARGUMENT, "head_dim must be <= 1024, got %d", p->head_dim);
-  if (p->causal && p->seqlen_kv < p->seqlen_q)
+  const bool varlen = p->cu_seqlens_q != nullptr;
+  if (varlen) {
+    if (!p->cu_seqlens_k) return set_error(FFPA_ERR_INVALID_ARGUMENT, "cu_seqlens_k must be set together with cu_seqlens_q");
+    if (p->total_q <= 0 || p->total_k <= 0) return set_error(FFPA_ERR_INVALID_ARGUMENT, "total_q / total_k must be positive in packed mode");
+    if (p->bias_kind != FFPA_BIAS_NONE || p->dropout_p > 0.f || p->fp8)
+      return set_error(FFPA_ERR_UNSUPPORTED, "packed variable-length mode supports neither attn bias, dropout nor fp8");
+  }
+  if (p->causal && !varlen && p->seqlen_kv < p->seqlen_q)
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "causal attention requires Nkv >= Nq (got Nq=%d, Nkv=%d)", p->seqlen_q, p->seqlen_kv);
   if (p->causal && p->bias_kind != FFPA_BIAS_NONE)
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "attn bias and causal masking are mutually exclusive");
@@ -153,8 +160,8 @@ int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream) {
   }
   if (!(p->dropout_p >= 0.f && p->dropout_p < 1.f))
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "dropout_p must be in [0, 1), got %f", (double)p->dropout_p);
-  const int32_t qd[3] = {p->batch, p->heads_q, p->seqlen_q};
-  const int32_t kd[3] = {p->batch, p->heads_kv, p->seqlen_kv};
+  const int32_t qd[3] = {varlen ? 1 : p->batch, p->heads_q, varlen ? p->total_q : p->seqlen_q};
+  const int32_t kd[3] = {varlen ? 1 : p->batch, p->heads_kv, varlen ? p->total_k : p->seqlen_kv};
   if (int e = check_strides("Q", p->q_stride, qd)) return e;
   if (int e = check_strides("K", p->k_stride, kd)) return e;
   if (int e = check_strides("V", p->v_stride, kd)) return e;
@@ -185,10 +192,17 @@ int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream) {
   if (p->heads_q % p->heads_kv != 0)
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "Q heads (%d) must be an integer multiple of KV heads (%d)", p->heads_q, p->heads_kv);
   if (p->head_dim % 8 != 0) return set_error(FFPA_ERR_INVALID_ARGUMENT, "head_dim must be a multiple of 8, got %d", p->head_dim);
-  if (p->causal && p->seqlen_kv < p->seqlen_q)
+  const bool varlen = p->cu_seqlens_q != nullptr;
+  if (varlen) {
+    if (!p->cu_seqlens_k) return set_error(FFPA_ERR_INVALID_ARGUMENT, "cu_seqlens_k must be set together with cu_seqlens_q");
+    if (p->total_q <= 0 || p->total_k <= 0) return set_error(FFPA_ERR_INVALID_ARGUMENT, "total_q / total_k must be positive in packed mode");
+    if (p->bias_kind != FFPA_BIAS_NONE || p->dropout_p > 0.f || p->d_bias)
+      return set_error(FFPA_ERR_UNSUPPORTED, "packed variable-length mode supports neither attn bias nor dropout");
+  }
+  if (p->causal && !varlen && p->seqlen_kv < p->seqlen_q)
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "causal attention requires Nkv >= Nq");
-  if (p->head_dim > 512)
-    return set_error(FFPA_ERR_UNSUPPORTED, "backward kernels support head_dim <= 512 (got %d)", p->head_dim);
+  if (p->head_dim > 1024)
+    return set_error(FFPA_ERR_UNSUPPORTED, "backward kernels support head_dim <= 1024 (got %d)", p->head_dim);
   if (p->bias_kind != FFPA_BIAS_NONE) {
     if (p->causal) return set_error(FFPA_ERR_INVALID_ARGUMENT, "attn bias and causal masking are mutually exclusive");
     if (p->bias_kind != FFPA_BIAS_F32 && p->bias_kind != FFPA_BIAS_QDTYPE)
@@ -198,8 +212,8 @@ int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream) {
   }
   if (!(p->dropout_p >= 0.f && p->dropout_p < 1.f))
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "dropout_p must be in [0, 1), got %f", (double)p->dropout_p);
-  const int32_t qd[3] = {p->batch, p->heads_q, p->seqlen_q};
-  const int32_t kd[3] = {p->batch, p->heads_kv, p->seqlen_kv};
+  const int32_t qd[3] = {varlen ? 1 : p->batch, p->heads_q, varlen ? p->total_q : p->seqlen_q};
+  const int32_t kd[3] = {varlen ? 1 : p->batch, p->heads_kv, varlen ? p->total_k : p->seqlen_kv};
   if (int e = check_strides("Q", p->q_stride, qd)) return e;
   if (int e = check_strides("K", p->k_stride, kd)) return e;
   if (int e = check_strides("V", p->v_stride, kd)) return e;

@@ -61,9 +61,12 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   const int D = a.head_dim;
   const int nqk = (D + 63) / 64;
   CUtensorMap mq, mk, mv;
-  if (!make_map(&mq, a.q, a.q_stride, a.batch, a.heads_q, a.seqlen_q, D, 64, 64) ||
-      !make_map(&mk, a.k, a.k_stride, a.batch, a.heads_kv, a.seqlen_kv, D, 64, 64) ||
-      !make_map(&mv, a.v, a.v_stride, a.batch, a.heads_kv, a.seqlen_kv, D, 64, 128))
+  // packed variable-length mode: one [total tokens, H, D] tensor per operand (map batch extent 1)
+  const bool varlen = a.cu_seqlens_q != nullptr;
+  const int mb = varlen ? 1 : a.batch, mnq = varlen ? a.total_q : a.seqlen_q, mnk = varlen ? a.total_k : a.seqlen_kv;
+  if (!make_map(&mq, a.q, a.q_stride, mb, a.heads_q, mnq, D, 64, 64) ||
+      !make_map(&mk, a.k, a.k_stride, mb, a.heads_kv, mnk, D, 64, 64) ||
+      !make_map(&mv, a.v, a.v_stride, mb, a.heads_kv, mnk, D, 64, 128))
     return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed (strides must be multiples of 8 elements, base 16-byte aligned)");
 
   FwdKernelParams kp{};
@@ -84,7 +87,11 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   kp.kv_splits = 1;
   kp.part_o = nullptr;
   kp.part_lse = nullptr;
-  {
+  kp.cu_q = a.cu_seqlens_q;
+  kp.cu_k = a.cu_seqlens_k;
+  kp.total_q = a.total_q;
+  kp.total_k = a.total_k;
+  if (!varlen) {
     const int sp = fwd_kv_splits(a.batch, a.heads_q, a.seqlen_q, a.seqlen_kv, D);
     const uint64_t need = fwd_split_workspace_bytes(a.batch, a.heads_q, a.seqlen_q, a.seqlen_kv, D);
     if (sp > 1 && a.workspace != nullptr && a.workspace_bytes >= need && (reinterpret_cast<uintptr_t>(a.workspace) & 15u) == 0) {
@@ -100,7 +107,7 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   if (nclusters > kp.n_items) nclusters = kp.n_items;
   kp.sched = nullptr;
   kp.sched_stride = 0;
-  if (a.causal && kp.n_items > nclusters && kp.kv_splits == 1) {
+  if (a.causal && kp.n_items > nclusters && kp.kv_splits == 1 && !varlen) {
     // causal items differ in length: balance them over the persistent clusters (greedy LPT over a
     // head-major, longest-first order; table cached on the device per shape)
     std::vector<int> cost((size_t)kp.n_items);

@@ -103,10 +103,10 @@ struct Barriers {
   uint64_t m_full[4];
 };
 
-__device__ __forceinline__ int num_kv_tiles(const FwdKernelParams& p, int q0) {
-  int tc = (p.seqlen_kv + 127) >> 7;
-  if (p.causal) {
-    int lim = ((q0 + 127 + (p.seqlen_kv - p.seqlen_q)) >> 7) + 1;
+__device__ __forceinline__ int num_kv_tiles(int causal, int nq, int nkv, int q0) {
+  int tc = (nkv + 127) >> 7;
+  if (causal) {
+    int lim = ((q0 + 127 + (nkv - nq)) >> 7) + 1;
     tc = lim < tc ? lim : tc;
   }
   return tc < 1 ? 1 : tc;
@@ -122,7 +122,11 @@ __device__ __forceinline__ int next_item(const FwdKernelParams& p, uint32_t clus
 
 // decoded work item. With kv_splits > 1 (few query tiles, long KV: decode-like shapes) an item covers only
 // the KV tiles [tbeg, tbeg + T) and writes an fp32 partial (O_s, LSE_s) that merge_splits_kernel combines.
-struct FwdItem { int mt, pass, bh, split, tbeg, T; };
+// Packed variable-length mode (p.cu_q != nullptr; reference API ffpa_attn_varlen_func,
+// /root/reference/src/ffpa_attn/ffpa_attn_interface.py:192-279): `batch` counts sequences, the tensors are
+// [total tokens, H, D] (tensor-map batch extent 1), and the item carries its sequence's lengths and token
+// offsets read from cu_seqlens; query tiles past the end of a short sequence are empty items.
+struct FwdItem { int mt, pass, bh, split, tbeg, T; int nq, nkv, qoff, koff, bt; };
 template <int NPASS>
 __device__ __forceinline__ FwdItem decode_fwd_item(const FwdKernelParams& p, uint32_t item) {
   FwdItem it;
@@ -132,7 +136,19 @@ __device__ __forceinline__ FwdItem decode_fwd_item(const FwdKernelParams& p, uin
   rest /= NPASS;
   it.split = rest % p.kv_splits;
   it.bh = rest / p.kv_splits;
-  const int ttot = num_kv_tiles(p, it.mt * 128);
+  if (p.cu_q != nullptr) {
+    const int b = it.bh / p.heads_q;
+    // offsets are clamped to the packed extents so a malformed cu_seqlens can never address past the tensors
+    it.qoff = min(max(__ldg(p.cu_q + b), 0), p.total_q);
+    it.nq = min(__ldg(p.cu_q + b + 1), p.total_q) - it.qoff;
+    it.koff = min(max(__ldg(p.cu_k + b), 0), p.total_k);
+    it.nkv = max(min(__ldg(p.cu_k + b + 1), p.total_k) - it.koff, 0);
+    it.bt = 0;
+    if (it.mt * 128 >= it.nq) { it.tbeg = 0; it.T = 0; return it; }
+  } else {
+    it.nq = p.seqlen_q; it.nkv = p.seqlen_kv; it.qoff = 0; it.koff = 0; it.bt = it.bh / p.heads_q;
+  }
+  const int ttot = num_kv_tiles(p.causal, it.nq, it.nkv, it.mt * 128);
   if (p.kv_splits == 1) { it.tbeg = 0; it.T = ttot; }
   else {
     const int per = (ttot + p.kv_splits - 1) / p.kv_splits;
@@ -254,9 +270,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t item = (uint32_t)item_s;
         const FwdItem fi = decode_fwd_item<Cfg::NPASS>(p, item);
         const int mt = fi.mt, pass = fi.pass, bh = fi.bh;
-        const int h = bh % p.heads_q, b = bh / p.heads_q;
+        const int h = bh % p.heads_q, b = fi.bt;   // b: batch coordinate of the tensor maps
         const int hk = h / group;
-        const int q0 = mt * 128;
+        const int q0 = fi.qoff + mt * 128;         // token rows (packed mode: offset of the sequence)
         const int T = fi.T, tbeg = fi.tbeg;
         if (T <= 0) { --it; continue; }   // empty KV split: no barrier traffic (the for-increment re-adds 1)
         const int dv0 = pass * Cfg::DSLAB, dvw = Cfg::slab_w(pass);
@@ -267,7 +283,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           ptx::tma_load_4d_2sm(sQ + jb * 8192, &map_q, l_q_full, jb * 64, q0 + 64 * (int)rank, h, b);
         for (int step = 0; step < T + LA; ++step) {
           if (step < T) {
-            const int kv0 = (tbeg + step) * 128;
+            const int kv0 = fi.koff + (tbeg + step) * 128;
 #pragma unroll
             for (int ks = 0; ks < Cfg::KST; ++ks) {
               const uint32_t stage = kc % Cfg::NKS, n = kc / Cfg::NKS;
@@ -288,7 +304,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
           if (step >= LA) {
-            const int kv0 = (tbeg + step - LA) * 128;
+            const int kv0 = fi.koff + (tbeg + step - LA) * 128;
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
               if (256 * s >= dvw) break;
@@ -446,12 +462,13 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int q0 = mt * 128;
       const int T = fi.T, tbeg = fi.tbeg;
       const int dv0 = pass * Cfg::DSLAB, dvw = Cfg::slab_w(pass);
-      const int gq = q0 + 64 * (int)rank + (int)row;  // global query row of this thread
-      const int causal_lim = gq + (p.seqlen_kv - p.seqlen_q);  // last visible key when causal
+      const int gq = q0 + 64 * (int)rank + (int)row;  // query row of this thread inside its sequence
+      const int seq_q = fi.nq, seq_kv = fi.nkv;       // lengths of this item's sequence
+      const int causal_lim = gq + (seq_kv - seq_q);  // last visible key when causal
       float m = NEG_INF, l = 0.f;   // ALT: m = the max this thread's partial sum l is expressed against
       if (T <= 0) {
         // empty KV split (causal rows that end before this split starts): contributes nothing
-        if (p.part_lse != nullptr && wgi == 0 && kh == 0 && gq < p.seqlen_q)
+        if (p.part_lse != nullptr && wgi == 0 && kh == 0 && gq < seq_q)
           p.part_lse[(((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq] = NEG_INF;
         continue;
       }
@@ -481,12 +498,12 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             for (int j = 0; j < CPT; ++j) x[j] = __uint_as_float(sr[j]) * p.scale_log2;
           } else {
             const int64_t boff = (int64_t)b * p.bias_stride[0] + (int64_t)h * p.bias_stride[1] +
-                                 (int64_t)(gq < p.seqlen_q ? gq : 0) * p.bias_stride[2];
+                                 (int64_t)(gq < seq_q ? gq : 0) * p.bias_stride[2];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
               const int key = key0 + j;
               float bv = 0.f;
-              if (key < p.seqlen_kv) {
+              if (key < seq_kv) {
                 if (p.bias_kind == 1) bv = reinterpret_cast<const float*>(p.bias)[boff + key];
                 else if (BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[boff + key]);
                 else bv = __half2float(reinterpret_cast<const __half*>(p.bias)[boff + key]);
@@ -495,10 +512,10 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
         }
-        const bool tail = (ti * 128 + 128 > p.seqlen_kv);
-        const bool diag = p.causal && (ti * 128 + 127 > q0 + (p.seqlen_kv - p.seqlen_q));
+        const bool tail = (ti * 128 + 128 > seq_kv);
+        const bool diag = p.causal && (ti * 128 + 127 > q0 + (seq_kv - seq_q));
         if (tail || diag) {
-          const int lim = p.causal ? (causal_lim < p.seqlen_kv - 1 ? causal_lim : p.seqlen_kv - 1) : p.seqlen_kv - 1;
+          const int lim = p.causal ? (causal_lim < seq_kv - 1 ? causal_lim : seq_kv - 1) : seq_kv - 1;
 #pragma unroll
           for (int j = 0; j < CPT; ++j)
             if (key0 + j > lim) x[j] = NEG_INF;
@@ -561,7 +578,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           // (/root/reference/csrc/cuffpa/native/prefill.cuh:506-546)
           const float inv_keep = 1.f / (1.f - p.dropout_p);
           const uint64_t ebase = p.philox_offset +
-              ((uint64_t)((int64_t)b * p.heads_q + h) * (uint64_t)p.seqlen_q + (uint64_t)(gq < p.seqlen_q ? gq : 0)) * (uint64_t)p.seqlen_kv +
+              ((uint64_t)((int64_t)b * p.heads_q + h) * (uint64_t)seq_q + (uint64_t)(gq < seq_q ? gq : 0)) * (uint64_t)seq_kv +
               (uint64_t)key0;
           lsum = 0.f;
 #pragma unroll
@@ -681,9 +698,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if constexpr (CQ == 4) l_tot += (xl[4][row] + xl[5][row]) + (xl[6][row] + xl[7][row]);
         }
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-        const bool row_ok = gq < p.seqlen_q;
+        const bool row_ok = gq < seq_q;
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
-                        2 * ((int64_t)b * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)gq * p.o_stride[2]);
+                        2 * ((int64_t)fi.bt * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)(fi.qoff + gq) * p.o_stride[2]);
 #pragma unroll
         for (int s = 0; s < Cfg::NSLICE; ++s) {
           if (256 * s >= dvw) break;
@@ -730,6 +747,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           // natural-log LSE; rows without any visible key: O = 0, LSE = -inf
           const float lse = (l_tot > 0.f) ? (m * mul + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
           if (p.kv_splits > 1) p.part_lse[(((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq] = lse;
+          else if (p.cu_q != nullptr) p.lse[(int64_t)h * p.total_q + fi.qoff + gq] = lse;   // [Hq, total_q]
           else p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
         }
         ptx::tc_fence_before();

@@ -27,6 +27,10 @@ struct FwdKernelParams {
   int kv_splits;
   float* part_o;
   float* part_lse;
+  // packed variable-length mode (cu_q != nullptr): token offsets per sequence, LSE is [Hq, total_q]
+  const int* cu_q;
+  const int* cu_k;
+  int total_q, total_k;
 };
 
 namespace bwd {
@@ -53,6 +57,11 @@ struct BwdKernelParams {
   const int* sched;
   int sched_stride;
   int n_chunks, chunk_len;
+  int n_pass;     // output-column slab passes per item (2 when head_dim > 512, else 1)
+  // packed variable-length mode (cu_q != nullptr): seqlen_q / seqlen_kv are the maxima, batch = sequences
+  const int* cu_q;
+  const int* cu_k;
+  int total_q, total_k;
   float* out32;   // non-null: accumulate into fp32 [B, H, out_rows, D] instead of storing `out`
   int out_rows;
 };

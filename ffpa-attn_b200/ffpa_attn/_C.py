@@ -50,6 +50,8 @@ class _FwdParams(ctypes.Structure):
     ("softmax_scale", ctypes.c_float), ("dropout_p", ctypes.c_float),
     ("philox_seed", ctypes.c_uint64), ("philox_offset", ctypes.c_uint64),
     ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64),
+    ("cu_seqlens_q", ctypes.c_void_p), ("cu_seqlens_k", ctypes.c_void_p),
+    ("total_q", ctypes.c_int32), ("total_k", ctypes.c_int32),
   ]
 
 
@@ -70,6 +72,8 @@ class _BwdParams(ctypes.Structure):
     ("bias", ctypes.c_void_p), ("bias_stride", ctypes.c_int64 * 4), ("bias_kind", ctypes.c_int32),
     ("dropout_p", ctypes.c_float), ("philox_seed", ctypes.c_uint64), ("philox_offset", ctypes.c_uint64),
     ("d_bias", ctypes.c_void_p),
+    ("cu_seqlens_q", ctypes.c_void_p), ("cu_seqlens_k", ctypes.c_void_p),
+    ("total_q", ctypes.c_int32), ("total_k", ctypes.c_int32),
   ]
 
 
@@ -91,8 +95,8 @@ _lib.ffpa_b200_launch_count.restype = ctypes.c_uint64
 _lib.ffpa_b200_last_error.restype = ctypes.c_char_p
 
 ABI_VERSION = int(_lib.ffpa_b200_abi_version())
-if ABI_VERSION != 1:
-  raise ImportError(f"ffpa_attn._C: libffpa_b200.so ABI {ABI_VERSION} != 1")
+if ABI_VERSION != 2:
+  raise ImportError(f"ffpa_attn._C: libffpa_b200.so ABI {ABI_VERSION} != 2")
 
 # module attributes of the reference binding (ffpa_api.cc:283-305)
 CUDA_FWD_AVAILABLE = bool(_lib.ffpa_b200_fwd_available())
@@ -278,6 +282,91 @@ def ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, 
     p.d_bias = d_bias.data_ptr()
   else:
     p.d_bias = None
+  with torch.cuda.device(Q.device):
+    stream = torch.cuda.current_stream(Q.device).cuda_stream
+    rc = _lib.ffpa_b200_bwd(ctypes.byref(p), ctypes.c_void_p(stream))
+  if rc != 0:
+    _raise(rc)
+
+
+def _strides_thd(t: torch.Tensor):
+  """[T, H, D] packed tensor -> (b, h, n, d) element strides of the C ABI (batch stride unused)."""
+  return (ctypes.c_int64 * 4)(0, int(t.stride(1)), int(t.stride(0)), int(t.stride(2)))
+
+
+def _check_varlen(Q, K, V, cu_q, cu_k):
+  if Q.dim() != 3 or K.dim() != 3 or V.dim() != 3:
+    raise RuntimeError("ffpa_attn varlen: q/k/v must be packed [T, H, D] tensors")
+  if K.shape != V.shape or K.size(2) != Q.size(2):
+    raise RuntimeError("ffpa_attn varlen: k and v must share [T_k, H_kv, D] and q's head dim")
+  for cu in (cu_q, cu_k):
+    if cu.dtype != torch.int32 or cu.dim() != 1 or not cu.is_contiguous() or cu.device != Q.device:
+      raise RuntimeError("ffpa_attn varlen: cu_seqlens must be contiguous int32 1-D tensors on q's device")
+  if cu_q.numel() != cu_k.numel() or cu_q.numel() < 2:
+    raise RuntimeError("ffpa_attn varlen: cu_seqlens_q / cu_seqlens_k must both have B + 1 entries")
+
+
+def ffpa_attn_varlen_forward(Q, K, V, O, softmax_lse, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                             causal, softmax_scale) -> None:
+  """Packed variable-length forward in ONE launch (C ABI 2, ``ffpa_fwd_params.cu_seqlens_*``): Q/O
+  [T_q, Hq, D], K/V [T_k, Hkv, D], LSE fp32 [Hq, T_q]. ``cu_seqlens`` stay on the device (no host sync);
+  ``max_seqlen_*`` size the grid. Backend of ``ffpa_attn_varlen_func``
+  (/root/reference/src/ffpa_attn/ffpa_attn_interface.py:192-279)."""
+  _check_cuda(Q, K, V, O, cu_seqlens_q, cu_seqlens_k)
+  _check_varlen(Q, K, V, cu_seqlens_q, cu_seqlens_k)
+  if K.dtype != Q.dtype or V.dtype != Q.dtype or O.dtype != Q.dtype or O.shape != Q.shape:
+    raise RuntimeError("ffpa_attn varlen: Q/K/V/O must share one dtype and O the shape of Q")
+  for t in (Q, K, V, O):
+    if t.stride(2) != 1:
+      raise RuntimeError("ffpa_attn varlen: unit stride on the head dim is required")
+  p = _FwdParams()
+  p.q, p.k, p.v, p.o = Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr()
+  if softmax_lse is not None and softmax_lse.numel() > 0:
+    if softmax_lse.dtype != torch.float32 or not softmax_lse.is_contiguous() or \
+        tuple(softmax_lse.shape) != (Q.size(1), Q.size(0)):
+      raise RuntimeError("ffpa_attn varlen: softmax_lse must be contiguous fp32 [Hq, T_q]")
+    p.lse = softmax_lse.data_ptr()
+  p.q_stride, p.k_stride, p.v_stride, p.o_stride = _strides_thd(Q), _strides_thd(K), _strides_thd(V), _strides_thd(O)
+  p.bias_stride = (ctypes.c_int64 * 4)(0, 0, 0, 0)
+  p.batch, p.heads_q, p.heads_kv, p.head_dim = cu_seqlens_q.numel() - 1, Q.size(1), K.size(1), Q.size(2)
+  p.seqlen_q, p.seqlen_kv = int(max_seqlen_q), int(max_seqlen_k)
+  p.total_q, p.total_k = Q.size(0), K.size(0)
+  p.cu_seqlens_q, p.cu_seqlens_k = cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr()
+  p.dtype = _dtype_code(Q)
+  p.causal = int(causal)
+  p.softmax_scale = float(softmax_scale)
+  with torch.cuda.device(Q.device):
+    stream = torch.cuda.current_stream(Q.device).cuda_stream
+    rc = _lib.ffpa_b200_fwd(ctypes.byref(p), ctypes.c_void_p(stream))
+  if rc != 0:
+    _raise(rc)
+
+
+def ffpa_attn_varlen_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, cu_seqlens_q, cu_seqlens_k,
+                              max_seqlen_q, max_seqlen_k, causal, softmax_scale) -> None:
+  """Packed variable-length backward (preprocess + dQ + dK + dV launches for the whole batch)."""
+  _check_cuda(Q, K, V, O, dO, dQ, dK, dV, softmax_lse, cu_seqlens_q, cu_seqlens_k)
+  _check_varlen(Q, K, V, cu_seqlens_q, cu_seqlens_k)
+  p = _BwdParams()
+  p.q, p.k, p.v, p.o = Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr()
+  p.lse, p.d_o = softmax_lse.data_ptr(), dO.data_ptr()
+  p.dq, p.dk, p.dv = dQ.data_ptr(), dK.data_ptr(), dV.data_ptr()
+  for name, t in (("q_stride", Q), ("k_stride", K), ("v_stride", V), ("o_stride", O),
+                  ("do_stride", dO), ("dq_stride", dQ), ("dk_stride", dK), ("dv_stride", dV)):
+    if t.stride(2) != 1:
+      raise RuntimeError("ffpa_attn varlen backward: all tensors need unit stride on the head dim")
+    setattr(p, name, _strides_thd(t))
+  p.bias_stride = (ctypes.c_int64 * 4)(0, 0, 0, 0)
+  p.batch, p.heads_q, p.heads_kv, p.head_dim = cu_seqlens_q.numel() - 1, Q.size(1), K.size(1), Q.size(2)
+  p.seqlen_q, p.seqlen_kv = int(max_seqlen_q), int(max_seqlen_k)
+  p.total_q, p.total_k = Q.size(0), K.size(0)
+  p.cu_seqlens_q, p.cu_seqlens_k = cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr()
+  p.dtype = _dtype_code(Q)
+  p.causal = int(causal)
+  p.softmax_scale = float(softmax_scale)
+  nbytes = int(_lib.ffpa_b200_bwd_workspace_bytes(p.batch, p.heads_q, p.heads_kv, p.seqlen_q, p.seqlen_kv, p.head_dim))
+  ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=Q.device)
+  p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
   with torch.cuda.device(Q.device):
     stream = torch.cuda.current_stream(Q.device).cuda_stream
     rc = _lib.ffpa_b200_bwd(ctypes.byref(p), ctypes.c_void_p(stream))

@@ -143,6 +143,55 @@ def _bwd_cuda_ex_fake(Q, K, V, O, softmax_lse, dO, attn_bias, stages, causal, so
           torch.empty_like(V, memory_format=torch.contiguous_format), dbias)
 
 
+# packed variable-length ops (reference: ffpa_attn::_varlen_fwd_cute / _varlen_bwd_cute registered at
+# /root/reference/src/ffpa_attn/cute/__init__.py:466-571; here one sm_100a launch set for the whole batch,
+# cu_seqlens never leave the device)
+torch.library.define(
+  f"{_OP_NAMESPACE}::_varlen_fwd_cuda",
+  "(Tensor q, Tensor k, Tensor v, Tensor cu_seqlens_q, Tensor cu_seqlens_k, int max_seqlen_q, int max_seqlen_k, "
+  "int causal, float softmax_scale) -> (Tensor o, Tensor softmax_lse)",
+)
+
+
+@torch.library.impl(f"{_OP_NAMESPACE}::_varlen_fwd_cuda", "CUDA")
+def _varlen_fwd_cuda_torch_op(Q, K, V, cu_q, cu_k, max_q, max_k, causal, softmax_scale):
+  O = torch.empty_like(Q, memory_format=torch.contiguous_format)  # noqa: E741
+  softmax_lse = torch.empty(Q.size(1), Q.size(0), dtype=torch.float32, device=Q.device)
+  _cuda_ext.ffpa_attn_varlen_forward(Q, K, V, O, softmax_lse, cu_q, cu_k, max_q, max_k, causal, softmax_scale)
+  return O, softmax_lse
+
+
+@torch.library.register_fake(f"{_OP_NAMESPACE}::_varlen_fwd_cuda")
+def _varlen_fwd_cuda_fake(Q, K, V, cu_q, cu_k, max_q, max_k, causal, softmax_scale):
+  return (torch.empty_like(Q, memory_format=torch.contiguous_format),
+          Q.new_empty(Q.size(1), Q.size(0), dtype=torch.float32))
+
+
+torch.library.define(
+  f"{_OP_NAMESPACE}::_varlen_bwd_cuda",
+  "(Tensor q, Tensor k, Tensor v, Tensor o, Tensor softmax_lse, Tensor d_o, Tensor cu_seqlens_q, Tensor cu_seqlens_k, "
+  "int max_seqlen_q, int max_seqlen_k, int causal, float softmax_scale) -> (Tensor dq, Tensor dk, Tensor dv)",
+)
+
+
+@torch.library.impl(f"{_OP_NAMESPACE}::_varlen_bwd_cuda", "CUDA")
+def _varlen_bwd_cuda_torch_op(Q, K, V, O, softmax_lse, dO, cu_q, cu_k, max_q, max_k, causal, softmax_scale):
+  # tokens outside every sequence (none when cu_seqlens spans the tensors) keep a zero gradient
+  dQ = torch.zeros_like(Q, memory_format=torch.contiguous_format)
+  dK = torch.zeros_like(K, memory_format=torch.contiguous_format)
+  dV = torch.zeros_like(V, memory_format=torch.contiguous_format)
+  _cuda_ext.ffpa_attn_varlen_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, cu_q, cu_k, max_q, max_k,
+                                      causal, softmax_scale)
+  return dQ, dK, dV
+
+
+@torch.library.register_fake(f"{_OP_NAMESPACE}::_varlen_bwd_cuda")
+def _varlen_bwd_cuda_fake(Q, K, V, O, softmax_lse, dO, cu_q, cu_k, max_q, max_k, causal, softmax_scale):
+  return (torch.empty_like(Q, memory_format=torch.contiguous_format),
+          torch.empty_like(K, memory_format=torch.contiguous_format),
+          torch.empty_like(V, memory_format=torch.contiguous_format))
+
+
 def _ffpa_attn_forward_cuda(Q, K, V, O, attn_bias, stages, acc, causal, softmax_scale,
                             dropout_p=0.0, philox_seed=0, philox_offset=0, fp8_smooth_k=True,
                             fp8_smooth_v=False, fp8_q_quant_method=0, fp8_k_quant_method=0,

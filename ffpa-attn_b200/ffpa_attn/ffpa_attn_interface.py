@@ -57,25 +57,33 @@ def ffpa_attn_varlen_func(
   ``q`` [T_q, Hq, D], ``k``/``v`` [T_k, Hkv, D], int32 ``cu_seqlens_*`` of length B+1 starting at 0,
   lower-right causal per sequence, LSE ``[Hq, T_q]`` fp32 when ``return_lse``.
 
-  B200 build: every sequence is a zero-copy strided view handed to the dense sm_100a kernels (the tensor
-  maps honour the THD strides), so forward AND backward (autograd) work for every head dim the dense
-  path supports; the price is one launch set per sequence and one host read of ``cu_seqlens``.
-  A single-launch varlen kernel is listed as a next step in DESIGN.md.
+  B200 build: ONE launch set for the whole packed batch (``torch.ops.ffpa_attn._varlen_fwd_cuda`` /
+  ``_varlen_bwd_cuda`` -> C ABI 2 -> the same sm_100a kernels as the dense path, whose work items read
+  their sequence's token range from ``cu_seqlens`` on the device). ``cu_seqlens`` are never read on the
+  host -- no synchronisation, CUDA-graph capturable -- exactly like the reference, which validates only
+  dtypes and shapes (/root/reference/src/ffpa_attn/cute/__init__.py:466-571); ``max_seqlen_*`` size the
+  grid, so sequences longer than the stated maximum are a caller error. Forward and backward support every
+  head dim of the dense path (8..1024).
   """
   for name in _VARLEN_UNSUPPORTED:
     if name in kwargs and kwargs[name] is not None:
       raise NotImplementedError(f"ffpa_attn_varlen_func: option {name!r} is not supported")
-  backend_kw = {k_: kwargs.pop(k_) for k_ in ("backend", "forward_backend", "backward_backend") if k_ in kwargs}
+  for name in ("backend", "forward_backend", "backward_backend"):
+    val = kwargs.pop(name, None)
+    if val is not None and not (val == "cuda" or type(val).__name__ == "CUDABackend"):
+      raise ValueError(f"ffpa_attn_varlen_func: {name}={val!r}: the only backend of this build is 'cuda'")
   for name in _VARLEN_UNSUPPORTED:
     kwargs.pop(name, None)
   if kwargs:
     raise TypeError(f"ffpa_attn_varlen_func() got unexpected keyword argument(s): {', '.join(sorted(kwargs))}")
   if dropout_p != 0.0:
     raise NotImplementedError("ffpa_attn_varlen_func: dropout_p must be 0.0")
-  if q.dtype not in (torch.float16, torch.bfloat16):
-    raise TypeError(f"ffpa_attn_varlen_func only supports fp16/bf16, got {q.dtype}")
   if q.dim() != 3 or k.dim() != 3 or v.dim() != 3:
     raise ValueError("q/k/v must be packed THD tensors [T, H, D]")
+  if q.dtype not in (torch.float16, torch.bfloat16):
+    raise TypeError(f"ffpa_attn_varlen_func only supports fp16/bf16, got {q.dtype}")
+  if k.dtype != q.dtype or v.dtype != q.dtype:
+    raise TypeError("ffpa_attn_varlen_func: q/k/v must share one dtype")
   if k.shape != v.shape or k.size(2) != q.size(2):
     raise ValueError("k and v must share [T_k, H_kv, D] and q's head dim")
   if cu_seqlens_k is None:
@@ -89,54 +97,37 @@ def ffpa_attn_varlen_func(
     raise ValueError("cu_seqlens_q and cu_seqlens_k must describe the same batch size")
   if not enable_gqa and q.size(1) != k.size(1):
     raise ValueError("enable_gqa=False but H_q != H_kv")
-  cq, ck = cu_seqlens_q.tolist(), cu_seqlens_k.tolist()
-  if cq[0] != 0 or ck[0] != 0 or cq[-1] != q.size(0) or ck[-1] != k.size(0):
-    raise ValueError("cu_seqlens must start at 0 and end at the packed token count")
-  if any(b < a for a, b in zip(cq, cq[1:])) or any(b < a for a, b in zip(ck, ck[1:])):
-    raise ValueError("cu_seqlens must be non-decreasing")
-  scale = softmax_scale if softmax_scale is not None else q.size(-1) ** -0.5
-
-  out = torch.empty_like(q)
-  lse = torch.full((q.size(1), q.size(0)), float("-inf"), dtype=torch.float32, device=q.device) if return_lse else None
-  outs = []
-  for b in range(len(cq) - 1):
-    nq, nk = cq[b + 1] - cq[b], ck[b + 1] - ck[b]
-    if nq == 0:
-      continue
-    if nk == 0:
-      outs.append((b, None))
-      continue
-    if causal and nk < nq:
-      raise ValueError(f"causal varlen attention requires Nkv >= Nq per sequence (sequence {b}: {nq} vs {nk})")
-    qb = q[cq[b]:cq[b + 1]].transpose(0, 1).unsqueeze(0)   # [1, H, n, D] view over the THD storage
-    kb = k[ck[b]:ck[b + 1]].transpose(0, 1).unsqueeze(0)
-    vb = v[ck[b]:ck[b + 1]].transpose(0, 1).unsqueeze(0)
-    if return_lse and not torch.is_grad_enabled():
-      from .cuda import _ffpa_attn_forward_cuda
-
-      ob, lb = _ffpa_attn_forward_cuda(qb, kb, vb, None, None, 0, 1, int(causal), scale)
-      lse[:, cq[b]:cq[b + 1]] = lb[0]
-    else:
-      ob = ffpa_attn_func(qb, kb, vb, is_causal=causal, scale=scale, enable_gqa=enable_gqa, **backend_kw)
-      if return_lse:
-        from .cuda import _ffpa_attn_forward_cuda
-
-        with torch.no_grad():
-          _, lb = _ffpa_attn_forward_cuda(qb.detach(), kb.detach(), vb.detach(), None, None, 0, 1, int(causal), scale)
-        lse[:, cq[b]:cq[b + 1]] = lb[0]
-    outs.append((b, ob[0].transpose(0, 1)))
-  if torch.is_grad_enabled() and any(t.requires_grad for t in (q, k, v)):
-    pieces = []
-    for b in range(len(cq) - 1):
-      nq = cq[b + 1] - cq[b]
-      if nq == 0:
-        continue
-      match = [o for bb, o in outs if bb == b]
-      pieces.append(match[0] if match and match[0] is not None else q.new_zeros(nq, q.size(1), q.size(2)))
-    out = torch.cat(pieces, dim=0) if pieces else out
-  else:
-    out.zero_()
-    for b, ob in outs:
-      if ob is not None:
-        out[cq[b]:cq[b + 1]] = ob
+  if q.size(1) % k.size(1) != 0:
+    raise ValueError("H_q must be an integer multiple of H_kv")
+  if q.size(2) % 8 != 0 or q.size(2) > 1024:
+    raise NotImplementedError(f"ffpa_attn_varlen_func supports head_dim % 8 == 0 and <= 1024, got {q.size(2)}")
+  if q.size(0) == 0 or k.size(0) == 0:
+    out = torch.zeros_like(q)
+    lse = torch.full((q.size(1), q.size(0)), float("-inf"), dtype=torch.float32, device=q.device)
+    return (out, lse) if return_lse else out
+  scale = float(softmax_scale) if softmax_scale is not None else q.size(-1) ** -0.5
+  out, lse = _FFPAVarlenFunc.apply(q, k, v, cu_seqlens_q.contiguous(), cu_seqlens_k.contiguous(),
+                                   int(max_seqlen_q), int(max_seqlen_k), bool(causal), scale)
   return (out, lse) if return_lse else out
+
+
+class _FFPAVarlenFunc(torch.autograd.Function):
+  """Autograd glue of the packed path (reference: FFPAAttnVarlenFunc, functional.py:1218-1250)."""
+
+  @staticmethod
+  def forward(ctx, q, k, v, cu_q, cu_k, max_q, max_k, causal, scale):
+    qc, kc, vc = (t if t.stride(2) == 1 and t.stride(0) % 8 == 0 and t.stride(1) % 8 == 0 else t.contiguous()
+                  for t in (q, k, v))
+    out, lse = torch.ops.ffpa_attn._varlen_fwd_cuda(qc, kc, vc, cu_q, cu_k, max_q, max_k, int(causal), scale)
+    ctx.save_for_backward(qc, kc, vc, out, lse, cu_q, cu_k)
+    ctx.args = (max_q, max_k, int(causal), scale)
+    ctx.mark_non_differentiable(lse)
+    return out, lse
+
+  @staticmethod
+  def backward(ctx, d_o, _d_lse):
+    q, k, v, out, lse, cu_q, cu_k = ctx.saved_tensors
+    max_q, max_k, causal, scale = ctx.args
+    dq, dk, dv = torch.ops.ffpa_attn._varlen_bwd_cuda(q, k, v, out, lse, d_o.contiguous(), cu_q, cu_k,
+                                                     max_q, max_k, causal, scale)
+    return dq, dk, dv, None, None, None, None, None, None

@@ -313,8 +313,8 @@ class _FFPAAttnFunc(torch.autograd.Function):
     meta: FFPAAttnMeta = ctx.meta
     if not CUDA_BWD_AVAILABLE:
       raise NotImplementedError("the sm_100a backward kernels are not built into libffpa_b200.so")
-    if q.size(-1) > 512:
-      raise NotImplementedError("ffpa_attn backward supports head_dim <= 512 on sm_100a (TMEM capacity)")
+    if q.size(-1) > 1024:
+      raise NotImplementedError("ffpa_attn backward supports head_dim <= 1024 on sm_100a")
     bias = ctx.attn_bias
     p_drop = meta.attn_meta.dropout_p
     stages = meta.backward_meta.stages

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FFPA_B200_ABI_VERSION 1
+#define FFPA_B200_ABI_VERSION 2
 
 enum {
   FFPA_OK = 0,
@@ -80,6 +80,16 @@ typedef struct ffpa_fwd_params {
    * 256-byte aligned device memory; ignored (may be NULL) when fp8 == 0 */
   void* workspace;
   uint64_t workspace_bytes;
+  /* Packed variable-length mode (ABI 2; replaces the reference's ffpa_attn_varlen_func backend,
+   * /root/reference/src/ffpa_attn/ffpa_attn_interface.py:192-279). All NULL / 0 for the dense layout.
+   * When cu_seqlens_q != NULL: q/o are [total_q, Hq, D] and k/v [total_k, Hkv, D] (stride[1] = head,
+   * stride[2] = token, stride[0] ignored); batch = number of sequences; seqlen_q / seqlen_kv = the MAXIMUM
+   * per-sequence lengths; cu_seqlens_*: int32 DEVICE arrays of batch + 1 token offsets (never read on the
+   * host: no synchronisation); LSE is [Hq, total_q]; causal is bottom-right aligned per sequence (rows
+   * that see no key give O = 0, LSE = -inf). One launch for the whole batch. No bias / dropout / fp8. */
+  const int32_t* cu_seqlens_q;
+  const int32_t* cu_seqlens_k;
+  int32_t total_q, total_k;
 } ffpa_fwd_params;
 
 typedef struct ffpa_bwd_params {
@@ -112,6 +122,11 @@ typedef struct ffpa_bwd_params {
   uint64_t philox_seed;
   uint64_t philox_offset;
   float* d_bias;
+  /* packed variable-length mode, same conventions as ffpa_fwd_params (lse is [Hq, total_q]); no bias /
+   * dropout / d_bias */
+  const int32_t* cu_seqlens_q;
+  const int32_t* cu_seqlens_k;
+  int32_t total_q, total_k;
 } ffpa_bwd_params;
 
 /* replaces ffpa_attn_forward (/root/reference/csrc/cuffpa/ffpa_api.cc:86-239) */

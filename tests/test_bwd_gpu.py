@@ -211,14 +211,64 @@ def test_backward_dropout_replay(p_drop, causal):
   _cmp(vg.grad, rv, 2e-2, "dV")
 
 
+@pytest.mark.parametrize("D", [520, 576, 640, 768, 896, 1024])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_backward_large_headdims(D, dtype):
+  """head_dim in (512, 1024] (north star: headdim 64-1024 forward and backward): two output-slab
+  passes per item, A2 streamed through the ring (csrc/ffpa_bwd_sm100.cuh, BwdCfg::LARGE)."""
+  q, k, v, d_o = _mk(1, 2, 2, 256, 384, D, dtype, seed=10)
+  _check_against_oracle(q, k, v, d_o, False, dtype)
+
+
+@pytest.mark.parametrize("D", [640, 1024])
+@pytest.mark.parametrize("Nq,Nkv", [(130, 257), (3, 300), (500, 1000)])
+def test_backward_large_headdims_causal_gqa_tails(D, Nq, Nkv):
+  q, k, v, d_o = _mk(2, 4, 2, Nq, Nkv, D, torch.bfloat16, seed=11)
+  _check_against_oracle(q, k, v, d_o, True, torch.bfloat16, enable_gqa=True, tol=1e-1)
+  _check_against_oracle(q, k, v, d_o, False, torch.bfloat16, enable_gqa=True)
+
+
+def test_backward_large_headdim_bias_and_dropout():
+  """GENERAL variants at D=768: additive bias + dBias, then dropout replay."""
+  import ffpa_attn
+
+  B, H, Nq, Nkv, D = 1, 2, 130, 200, 768
+  q, k, v, d_o = _mk(B, H, H, Nq, Nkv, D, torch.bfloat16, seed=12)
+  bias = torch.randn(B, H, Nq, Nkv, generator=torch.Generator().manual_seed(3)).to(DEV).requires_grad_(True)
+  qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+  ffpa_attn.ffpa_attn_func(qg, kg, vg, attn_mask=bias).backward(d_o)
+  torch.cuda.synchronize()
+  rq, rk, rv, rds = orc.attention_bwd(q.cpu(), k.cpu(), v.cpu(), d_o.cpu(), bias=bias.detach().cpu().double().numpy())
+  for got, want, name in ((qg.grad, rq, "dQ"), (kg.grad, rk, "dK"), (vg.grad, rv, "dV"), (bias.grad, rds, "dBias")):
+    _cmp(got, want, 5e-2, name)
+  torch.cuda.manual_seed(4321)
+  seed, offset = int(torch.cuda.initial_seed()), int(torch.cuda._get_rng_state_offset())
+  qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+  ffpa_attn.ffpa_attn_func(qg, kg, vg, dropout_p=0.1).backward(d_o)
+  torch.cuda.synchronize()
+  rq, rk, rv, _ = orc.attention_bwd(q.cpu(), k.cpu(), v.cpu(), d_o.cpu(), dropout_p=0.1, philox_seed=seed, philox_offset=offset)
+  for got, want, name in ((qg.grad, rq, "dQ"), (kg.grad, rk, "dK"), (vg.grad, rv, "dV")):
+    _cmp(got, want, 5e-2, name)
+
+
+def test_backward_large_headdim_full_length_sampled_head():
+  """BASELINE config 5's largest head dim in the backward: N=4096 D=1024 bf16 against fp32 torch on the GPU."""
+  q, k, v, d_o = _mk(1, 2, 2, 4096, 4096, 1024, torch.bfloat16, seed=13)
+  _, dq, dk, dv = _grads(q, k, v, d_o, is_causal=True)
+  rq, rk, rv = _torch_ref_grads(q[:, 1:], k[:, 1:], v[:, 1:], d_o[:, 1:], True)
+  for got, want, name in ((dq[:, 1:], rq, "dQ"), (dk[:, 1:], rk, "dK"), (dv[:, 1:], rv, "dV")):
+    err = (got.float() - want).abs().max().item()
+    assert err < 1e-1 * max(1.0, want.abs().max().item()), f"{name}: {err}"
+    cos = torch.nn.functional.cosine_similarity(got.float().flatten(), want.flatten(), dim=0).item()
+    assert cos > 0.999, f"{name}: cosine {cos}"
+
+
 def test_backward_rejects_unsupported():
   import ffpa_attn
 
-  q, k, v, d_o = _mk(1, 2, 2, 128, 128, 768, torch.bfloat16)
-  q.requires_grad_(True)
-  out = ffpa_attn.ffpa_attn_func(q, k, v)
-  with pytest.raises(NotImplementedError):
-    out.backward(d_o)
+  q = torch.randn(1, 1, 128, 1032, dtype=torch.bfloat16, device=DEV)
+  with pytest.raises((NotImplementedError, ValueError, RuntimeError)):
+    ffpa_attn.ffpa_attn_func(q, q, q)
 
 
 @pytest.mark.parametrize("Nq", [1, 2, 3, 4, 7])

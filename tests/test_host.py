@@ -46,7 +46,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_flags(lib):
   lib.ffpa_b200_abi_version.restype = ctypes.c_int32
-  assert lib.ffpa_b200_abi_version() == 1
+  assert lib.ffpa_b200_abi_version() == 2
   assert lib.ffpa_b200_fwd_available() == 1
 
 
@@ -58,13 +58,15 @@ def test_ctypes_struct_layout_matches_c():
 #include <stddef.h>
 #include "ffpa_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(ffpa_fwd_params), offsetof(ffpa_fwd_params, bias_stride),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ffpa_fwd_params), offsetof(ffpa_fwd_params, bias_stride),
          offsetof(ffpa_fwd_params, batch), offsetof(ffpa_fwd_params, softmax_scale),
          offsetof(ffpa_fwd_params, philox_seed), offsetof(ffpa_fwd_params, philox_offset),
-         offsetof(ffpa_fwd_params, workspace_bytes));
-  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ffpa_bwd_params), offsetof(ffpa_bwd_params, batch),
+         offsetof(ffpa_fwd_params, workspace_bytes), offsetof(ffpa_fwd_params, cu_seqlens_q),
+         offsetof(ffpa_fwd_params, total_k));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ffpa_bwd_params), offsetof(ffpa_bwd_params, batch),
          offsetof(ffpa_bwd_params, softmax_scale), offsetof(ffpa_bwd_params, workspace),
-         offsetof(ffpa_bwd_params, bias_kind), offsetof(ffpa_bwd_params, d_bias));
+         offsetof(ffpa_bwd_params, bias_kind), offsetof(ffpa_bwd_params, d_bias),
+         offsetof(ffpa_bwd_params, cu_seqlens_k), offsetof(ffpa_bwd_params, total_q));
   return 0;
 }
 """
@@ -77,8 +79,9 @@ int main(void) {
   F, B = C._FwdParams, C._BwdParams
   want = [ctypes.sizeof(F), F.bias_stride.offset, F.batch.offset, F.softmax_scale.offset,
           F.philox_seed.offset, F.philox_offset.offset, F.workspace_bytes.offset,
+          F.cu_seqlens_q.offset, F.total_k.offset,
           ctypes.sizeof(B), B.batch.offset, B.softmax_scale.offset, B.workspace.offset,
-          B.bias_kind.offset, B.d_bias.offset]
+          B.bias_kind.offset, B.d_bias.offset, B.cu_seqlens_k.offset, B.total_q.offset]
   assert [int(x) for x in out] == want
 
 

@@ -65,10 +65,82 @@ def test_varlen_validation_errors():
     ffpa_attn.ffpa_attn_varlen_func(q, k, v, cq, ck, 64, 64, window_size=(8, 8))
   with pytest.raises(ValueError):
     ffpa_attn.ffpa_attn_varlen_func(q, k[:, :1], v[:, :1], cq, ck, 64, 64)
+  with pytest.raises(ValueError):  # batch-size mismatch between the two offset vectors
+    ffpa_attn.ffpa_attn_varlen_func(q, k, v, cq[:-1], ck, 64, 64)
+  # like the reference, cu_seqlens VALUES are never read on the host; a malformed vector is clamped to the
+  # packed extent on the device instead of addressing past the tensors
   bad = cq.clone()
-  bad[-1] += 1
-  with pytest.raises(ValueError):
-    ffpa_attn.ffpa_attn_varlen_func(q, k, v, bad, ck, 64, 64)
+  bad[-1] += 64
+  out = ffpa_attn.ffpa_attn_varlen_func(q, k, v, bad, ck, 128, 64)
+  torch.cuda.synchronize()
+  assert torch.isfinite(out.float()).all()
+
+
+def test_varlen_single_launch_many_sequences_and_graph_capture():
+  """One forward launch and four backward launches for the whole packed batch (no per-sequence dispatch,
+  no host read of cu_seqlens): launch counter + CUDA-graph capture + empty sequences + D = 1024."""
+  import ffpa_attn
+
+  lens_q = [5, 0, 129, 300, 64, 17, 256, 1]
+  lens_k = [5, 40, 129, 0, 200, 17, 512, 9]
+  q, k, v, cq, ck = _pack(lens_q, lens_k, 4, 4, 256, torch.float16, seed=2)
+  n0 = ffpa_attn._C.launch_count()
+  out, lse = ffpa_attn.ffpa_attn_varlen_func(q, k, v, cq, ck, 300, 512, causal=False, return_lse=True)
+  torch.cuda.synchronize()
+  assert ffpa_attn._C.launch_count() - n0 == 1
+  cql, ckl = cq.tolist(), ck.tolist()
+  for b in range(len(lens_q)):
+    sq, sk = slice(cql[b], cql[b + 1]), slice(ckl[b], ckl[b + 1])
+    if lens_q[b] == 0:
+      continue
+    if lens_k[b] == 0:   # no key: O = 0, LSE = -inf (SM100 convention, _fwd_d512_sm100.py:2635-2646)
+      assert out[sq].float().abs().max().item() == 0.0 and torch.isinf(lse[:, sq]).all()
+      continue
+    ref, lref = orc.attention_fwd(q[sq].transpose(0, 1)[None].cpu(), k[sk].transpose(0, 1)[None].cpu(),
+                                  v[sk].transpose(0, 1)[None].cpu())
+    assert np.abs(out[sq].transpose(0, 1)[None].float().cpu().numpy() - ref).max() < 1e-2
+    assert np.abs(lse[:, sq].cpu().numpy() - lref[0]).max() < 2e-3
+  # graph capture: nothing on the path synchronises
+  g = torch.cuda.CUDAGraph()
+  static_out = None
+  s = torch.cuda.Stream()
+  s.wait_stream(torch.cuda.current_stream())
+  with torch.cuda.stream(s):
+    ffpa_attn.ffpa_attn_varlen_func(q, k, v, cq, ck, 300, 512)
+  torch.cuda.current_stream().wait_stream(s)
+  with torch.cuda.graph(g):
+    static_out = ffpa_attn.ffpa_attn_varlen_func(q, k, v, cq, ck, 300, 512)
+  g.replay()
+  torch.cuda.synchronize()
+  assert torch.equal(static_out, out)
+
+
+@pytest.mark.parametrize("D", [64, 320, 1024])
+def test_varlen_causal_cross_lengths_and_head_dims(D):
+  """Per-sequence bottom-right causal incl. Nkv < Nq sequences (leading rows see no key -> O = 0, zero
+  gradients), forward + backward in packed mode."""
+  import ffpa_attn
+
+  lens_q, lens_k = [100, 260, 33], [228, 260, 20]
+  q, k, v, cq, ck = _pack(lens_q, lens_k, 2, 1, D, torch.bfloat16, seed=4)
+  qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+  d_o = torch.randn_like(q)
+  n0 = ffpa_attn._C.launch_count()
+  og = ffpa_attn.ffpa_attn_varlen_func(qg, kg, vg, cq, ck, 260, 260, causal=True, enable_gqa=True)
+  og.backward(d_o)
+  torch.cuda.synchronize()
+  assert ffpa_attn._C.launch_count() - n0 == 5   # fwd + preprocess + dQ + dK + dV
+  cql, ckl = cq.tolist(), ck.tolist()
+  for b in range(len(lens_q)):
+    sq, sk = slice(cql[b], cql[b + 1]), slice(ckl[b], ckl[b + 1])
+    qb, kb, vb = (t.transpose(0, 1)[None].cpu() for t in (q[sq], k[sk], v[sk]))
+    ref, _ = orc.attention_fwd(qb, kb, vb, causal=True)
+    assert np.abs(og[sq].transpose(0, 1)[None].detach().float().cpu().numpy() - ref).max() < 2e-2
+    rq, rk, rv, _ = orc.attention_bwd(qb, kb, vb, d_o[sq].transpose(0, 1)[None].cpu(), causal=True)
+    for got_g, want in ((qg.grad[sq].transpose(0, 1)[None], rq), (kg.grad[sk].transpose(0, 1)[None], rk),
+                        (vg.grad[sk].transpose(0, 1)[None], rv)):
+      err = np.abs(got_g.float().cpu().numpy() - want).max()
+      assert err < 1e-1 * max(1.0, np.abs(want).max())
 
 
 @pytest.mark.parametrize("causal,Hkv,chunks", [(False, 4, 8), (True, 2, 2), (False, 4, 3)])
