@@ -1,6 +1,7 @@
 // Host launcher of the backward: preprocess (delta, lse2) + dQ + dK + dV kernels on one stream.
 // Implements the symbol the reference leaves as a thrower
 // (/root/reference/csrc/cuffpa/ffpa_api.cc:242-263).
+#include <cstdlib>
 #include <vector>
 #include "ffpa_internal.h"
 #include "sm100_ptx.cuh"
@@ -13,6 +14,11 @@ int dispatch_bwd_dtype(int nqk, int kind, const CUtensorMap& a1, const CUtensorM
                        cudaStream_t stream);
 template <bool BF16>
 int launch_preprocess(const ffpa_bwd_params& a, float* lse2, float* delta, int nq_pad, cudaStream_t stream);
+template <bool BF16>
+int launch_bwd_gemm(const CUtensorMap& map_t, const CUtensorMap& map_b, const BwdGemmParams& kp, int nclusters,
+                    cudaStream_t stream);
+extern template int launch_bwd_gemm<true>(const CUtensorMap&, const CUtensorMap&, const BwdGemmParams&, int, cudaStream_t);
+extern template int launch_bwd_gemm<false>(const CUtensorMap&, const CUtensorMap&, const BwdGemmParams&, int, cudaStream_t);
 extern template int dispatch_bwd_dtype<true>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
                                              const CUtensorMap&, const CUtensorMap&, const BwdKernelParams&, int, cudaStream_t);
 extern template int dispatch_bwd_dtype<false>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
@@ -41,12 +47,39 @@ static bool may_split_kv(int batch, int heads_kv, int seqlen_kv) {
   return kv_items < 8ll * (sm_count() / 2);
 }
 
-uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
+// Stash path (ffpa_bwd_gemm_sm100.cuh): bytes of ONE 16-bit [B, Hq, nq_pad, nk_pad] score buffer (two are
+// needed: P_drop and dS), or 0 when the path does not apply. It pays when a GEMM pass over the head dim costs
+// more than moving the N x N tile through HBM: head dims 384..512 (above, the accumulator of the GEMM-only
+// kernel no longer fits TMEM). FFPA_BWD_STASH=0 disables it, FFPA_BWD_STASH_MAX_GB (default 20) bounds both
+// buffers together; beyond the bound the three recompute kernels run.
+static uint64_t bwd_stash_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
+  if (head_dim < 384 || head_dim > 512) return 0;
+  static int enabled = -1;
+  static double max_gb = 20.0;
+  if (enabled < 0) {
+    const char* e = getenv("FFPA_BWD_STASH");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+    const char* g = getenv("FFPA_BWD_STASH_MAX_GB");
+    if (g) max_gb = atof(g);
+  }
+  if (!enabled) return 0;
+  const uint64_t nq_pad = ((uint64_t)seqlen_q + 127) / 128 * 128, nk_pad = ((uint64_t)seqlen_kv + 255) / 256 * 256;
+  const uint64_t one = align256((uint64_t)batch * heads_q * nq_pad * nk_pad * 2);
+  if (2.0 * (double)one > max_gb * 1073741824.0) return 0;
+  return one;
+}
+
+uint64_t bwd_workspace_bytes_min(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
   const uint64_t nq_pad = ((uint64_t)seqlen_q + 127) / 128 * 128;
   uint64_t total = align256(2ull * batch * heads_q * nq_pad * sizeof(float));
   if (may_split_kv(batch, heads_kv, seqlen_kv))
     total += 2 * align256((uint64_t)batch * heads_kv * seqlen_kv * head_dim * sizeof(float));
   return total;
+}
+
+uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
+  return bwd_workspace_bytes_min(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim) +
+         2 * bwd_stash_bytes(batch, heads_q, seqlen_q, seqlen_kv, head_dim);
 }
 
 template <bool BF16>
@@ -121,6 +154,13 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   kp.cu_q = a.cu_seqlens_q;
   kp.cu_k = a.cu_seqlens_k;
   kp.total_q = a.total_q; kp.total_k = a.total_k;
+  // stash path: the dQ kernel writes P_drop / dS tiles, dK and dV become plain GEMMs over them
+  const uint64_t stash_one = varlen ? 0 : bwd_stash_bytes(B, Hq, Nq, Nkv, D);
+  const uint64_t stash_at = bwd_workspace_bytes_min(B, Hq, Hkv, Nq, Nkv, D);
+  const bool use_stash = stash_one > 0 && a.workspace_bytes >= stash_at + 2 * stash_one;
+  const int nk_pad = (Nkv + 255) / 256 * 256;
+  void* stash_p = use_stash ? static_cast<uint8_t*>(a.workspace) + stash_at : nullptr;
+  void* stash_ds = use_stash ? static_cast<uint8_t*>(a.workspace) + stash_at + stash_one : nullptr;
   const int max_clusters = sm_count() / 2;
   const int off = Nkv - Nq;
   auto run = [&](int kind, void* out, const int64_t* ostride, int rows, int heads, float* acc32,
@@ -130,6 +170,9 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
     for (int i = 0; i < 3; ++i) kp.out_stride[i] = ostride[i];
     kp.n_rtiles = (rows + 127) / 128;
     kp.out_rows = rows;
+    kp.stash_p = kind == 0 ? stash_p : nullptr;
+    kp.stash_ds = kind == 0 ? stash_ds : nullptr;
+    kp.nk_pad = nk_pad;
     // streamed tiles per item (same rule as col_tiles<KIND> in the kernel)
     const int group = Hq / Hkv;
     const int tq = (Nq + 127) / 128, tk = (Nkv + 127) / 128;
@@ -140,7 +183,11 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
       int t;
       if (kind == 0) {
         t = tk;
-        if (a.causal) { const int lim = ((rt * 128 + 127 + off) >> 7) + 1; t = lim < t ? lim : t; }
+        if (a.causal) {
+          int lim = ((rt * 128 + 127 + off) >> 7) + 1;
+          if (use_stash) { lim = (lim + 1) & ~1; t = (t + 1) & ~1; }   // same pairing rule as col_tiles<dQ>
+          t = lim < t ? lim : t;
+        }
         t = t < 1 ? 1 : t;
       } else {
         int first = 0;
@@ -198,6 +245,41 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
     return FFPA_OK;
   };
   if ((rc = run(0, a.dq, a.dq_stride, Nq, Hq, nullptr, q_km, do_km, k_km, v_km, k_mn))) return rc;
+  if (use_stash) {
+    CUtensorMap st_p, st_ds;
+    const int64_t sstr[3] = {(int64_t)Hq * nq_pad * nk_pad, (int64_t)nq_pad * nk_pad, (int64_t)nk_pad};
+    if (!make_map4(&st_p, stash_p, sstr, B, Hq, nq_pad, nk_pad, 64, 128) ||
+        !make_map4(&st_ds, stash_ds, sstr, B, Hq, nq_pad, nk_pad, 64, 128))
+      return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the backward stash");
+    bwd::BwdGemmParams gp{};
+    gp.batch = B; gp.heads_q = Hq; gp.heads_kv = Hkv; gp.seqlen_q = Nq; gp.seqlen_kv = Nkv; gp.head_dim = D;
+    gp.causal = a.causal;
+    gp.n_kblocks = nk_pad / 256;
+    gp.n_items = gp.n_kblocks * B * Hkv;
+    const int ncl = gp.n_items < max_clusters ? gp.n_items : max_clusters;
+    gp.sched = nullptr;
+    gp.sched_stride = 0;
+    if (a.causal && gp.n_items > ncl) {
+      const int tq = (Nq + 127) / 128, group = Hq / Hkv;
+      std::vector<int> cost((size_t)gp.n_items);
+      for (int it = 0; it < gp.n_items; ++it) {
+        const int qmin = (it % gp.n_kblocks) * 256 - off;
+        int first = qmin > 0 ? (qmin >> 7) : 0;
+        first = first > tq ? tq : first;
+        const int t = (tq - first) * group;
+        cost[it] = t > 0 ? t * 16 + 24 : 1;
+      }
+      gp.sched = get_schedule(cost.data(), gp.n_items, ncl, &gp.sched_stride, stream);
+    }
+    auto gemm = [&](const CUtensorMap& mt, const CUtensorMap& mb, void* out, const int64_t* ostride, float mul) -> int {
+      gp.out = out;
+      for (int i = 0; i < 3; ++i) gp.out_stride[i] = ostride[i];
+      gp.mul = mul;
+      return bf16 ? bwd::launch_bwd_gemm<true>(mt, mb, gp, ncl, stream) : bwd::launch_bwd_gemm<false>(mt, mb, gp, ncl, stream);
+    };
+    if ((rc = gemm(st_p, do_mn, a.dv, a.dv_stride, 1.f))) return rc;
+    return gemm(st_ds, q_mn, a.dk, a.dk_stride, a.softmax_scale);
+  }
   if ((rc = run(1, a.dk, a.dk_stride, Nkv, Hkv, dk32, k_km, v_km, q_km, do_km, q_mn))) return rc;
   if ((rc = run(2, a.dv, a.dv_stride, Nkv, Hkv, dv32, k_km, k_km, q_km, q_km, do_mn))) return rc;
   return FFPA_OK;

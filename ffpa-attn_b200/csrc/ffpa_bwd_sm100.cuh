@@ -97,11 +97,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr) {
 struct TileRange { int first, count; };
 
 template <int KIND>
-__device__ __forceinline__ TileRange col_tiles(int causal, int nq, int nkv, int r0) {
+__device__ __forceinline__ TileRange col_tiles(int causal, int nq, int nkv, int r0, bool stash = false) {
   if (KIND == kKindDQ) {  // rows = queries starting at r0; columns = KV tiles
     int tc = (nkv + 127) >> 7;
     if (causal) {
       int lim = ((r0 + 127 + (nkv - nq)) >> 7) + 1;
+      // stash path: the GEMM-only dK/dV kernel consumes 256-key blocks, so visit KV tiles in pairs (the
+      // extra tile is fully masked and stores zeros)
+      if (stash) { lim = (lim + 1) & ~1; tc = (tc + 1) & ~1; }
       tc = lim < tc ? lim : tc;
     }
     return {0, tc < 1 ? 1 : tc};
@@ -145,7 +148,7 @@ __device__ __forceinline__ Item decode_item(const BwdKernelParams& p, int item, 
   } else {
     it.nq = p.seqlen_q; it.nkv = p.seqlen_kv; it.qoff = 0; it.koff = 0; it.bt = b;
   }
-  it.tr = col_tiles<KIND>(p.causal, it.nq, it.nkv, it.rt * 128);
+  it.tr = col_tiles<KIND>(p.causal, it.nq, it.nkv, it.rt * 128, KIND == kKindDQ && p.stash_ds != nullptr);
   const int tfull = it.tr.count * n_inner;
   if (p.n_chunks == 1) { it.s0 = 0; it.n = tfull; }
   else {
@@ -484,13 +487,17 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           if (p.causal) lim_lo = grow - off;
         }
         uint32_t pk[16];
+        uint32_t pp[4];   // stash path: packed P_drop of the current group of 8 columns
+        const bool stash = (KIND == kKindDQ) && p.stash_ds != nullptr;
         // GENERAL: additive bias, Philox dropout replay, dBias output (dQ kind). Query / key of
         // element jj: dQ kind (q = grow, key = col), dK/dV kinds (q = col, key = grow).
         const int hq_cur = (KIND == kKindDQ) ? hs : hs * group + gi;
         const float inv_keep = GENERAL ? 1.f / (1.f - p.dropout_p) : 1.f;
+        // stash row of this thread: [b, hq, grow, col0 ..] (16-bit elements; col0 is a multiple of 32)
+        const int64_t stash_off = stash ? ((((int64_t)b * p.heads_q + hq_cur) * p.nq_pad + grow) * (int64_t)p.nk_pad + col0) : 0;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float e[2];
+          float e[2], pv[2] = {0.f, 0.f};
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int jj = j + u;
@@ -533,6 +540,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             if (HAS_DP) {
               const float ds = pe * (__uint_as_float(dr[jj]) * mult - dl);
               e[u] = ds;
+              if (KIND == kKindDQ) pv[u] = pe * mult;   // P_drop (what dV consumes), only used by the stash path
               if constexpr (GENERAL && KIND == kKindDQ) {
                 if (p.dbias != nullptr && itm.pass == 0 && qi < seq_q && ki < seq_kv)
                   p.dbias[(((int64_t)b * p.heads_q + hq_cur) * p.seqlen_q + qi) * (int64_t)p.seqlen_kv + ki] = ds;
@@ -542,6 +550,15 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             }
           }
           pk[j >> 1] = BF16 ? ptx::pack_bf16x2(e[0], e[1]) : ptx::pack_f16x2(e[0], e[1]);
+          if (KIND == kKindDQ) {
+            pp[(j >> 1) & 3] = BF16 ? ptx::pack_bf16x2(pv[0], pv[1]) : ptx::pack_f16x2(pv[0], pv[1]);
+            if (stash && (j & 6) == 6) {   // 8 columns complete: one 16-byte store each for P_drop and dS
+              const int64_t so = stash_off + (j - 6);
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.stash_p) + so) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.stash_ds) + so) =
+                  make_uint4(pk[(j >> 1) - 3], pk[(j >> 1) - 2], pk[(j >> 1) - 1], pk[j >> 1]);
+            }
+          }
         }
         ptx::mbar_wait(bar(bars.t_empty[sbuf]), ((g >> 1) & 1) ^ 1);
         {

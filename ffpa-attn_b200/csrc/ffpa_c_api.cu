@@ -233,6 +233,11 @@ uint64_t ffpa_b200_bwd_workspace_bytes(int32_t batch, int32_t heads_q, int32_t h
   return bwd_workspace_bytes(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
 }
 
+uint64_t ffpa_b200_bwd_workspace_bytes_min(int32_t batch, int32_t heads_q, int32_t heads_kv, int32_t seqlen_q,
+                                           int32_t seqlen_kv, int32_t head_dim) {
+  return bwd_workspace_bytes_min(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
+}
+
 int ffpa_b200_set_backend_impl(int32_t impl) {
   if (impl < FFPA_IMPL_AUTO || impl > FFPA_IMPL_CUTE_TMA_FP4)
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "backend impl hint %d out of range", impl);

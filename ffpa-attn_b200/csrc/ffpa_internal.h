@@ -62,8 +62,24 @@ struct BwdKernelParams {
   const int* cu_q;
   const int* cu_k;
   int total_q, total_k;
+  // stash path (dQ kind, large head dims): P_drop and dS tiles as 16-bit [B, Hq, nq_pad, nk_pad] for the
+  // GEMM-only dK / dV kernel (ffpa_bwd_gemm_sm100.cuh); nullptr = off
+  void* stash_p;
+  void* stash_ds;
+  int nk_pad;
   float* out32;   // non-null: accumulate into fp32 [B, H, out_rows, D] instead of storing `out`
   int out_rows;
+};
+// GEMM-only dK / dV kernel over stashed score tiles (256 keys per 2-CTA cluster)
+struct BwdGemmParams {
+  void* out;               // dK or dV
+  int64_t out_stride[3];
+  int batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
+  int causal;
+  float mul;               // softmax_scale for dK, 1 for dV
+  int n_kblocks, n_items;  // 256-key blocks per (b, kv head); items = n_kblocks * B * Hkv
+  const int* sched;
+  int sched_stride;
 };
 }  // namespace bwd
 
@@ -82,5 +98,7 @@ uint64_t fwd_split_workspace_bytes(int batch, int heads_q, int seqlen_q, int seq
 uint64_t fwd_fp8_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim);
 uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv,
                              int head_dim);
+uint64_t bwd_workspace_bytes_min(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv,
+                                 int head_dim);
 
 }  // namespace ffpa

@@ -85,6 +85,8 @@ _lib.ffpa_b200_fwd_workspace_bytes.argtypes = [ctypes.c_int32] * 7
 _lib.ffpa_b200_fwd_workspace_bytes.restype = ctypes.c_uint64
 _lib.ffpa_b200_bwd_workspace_bytes.argtypes = [ctypes.c_int32] * 6
 _lib.ffpa_b200_bwd_workspace_bytes.restype = ctypes.c_uint64
+_lib.ffpa_b200_bwd_workspace_bytes_min.argtypes = [ctypes.c_int32] * 6
+_lib.ffpa_b200_bwd_workspace_bytes_min.restype = ctypes.c_uint64
 _lib.ffpa_b200_set_backend_impl.argtypes = [ctypes.c_int32]
 _lib.ffpa_b200_set_backend_impl.restype = ctypes.c_int
 _lib.ffpa_b200_get_backend_impl.restype = ctypes.c_int32
@@ -247,7 +249,8 @@ def ffpa_attn_forward(Q, K, V, attn_bias, O, softmax_lse, stages, acc, causal, s
 
 
 def ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale,
-                       attn_bias=None, dropout_p=0.0, philox_seed=0, philox_offset=0, d_bias=None) -> None:
+                       attn_bias=None, dropout_p=0.0, philox_seed=0, philox_offset=0, d_bias=None,
+                       min_workspace=False) -> None:
   """Positional signature of ffpa_api.cc:242-246 (a thrower in the reference); real here.
   Keyword extras replay what the forward applied: additive ``attn_bias``, dropout (same Philox
   seed/offset) and ``d_bias`` -- an fp32 [B, Hq, Nq, Nkv] buffer that receives dS per score."""
@@ -267,8 +270,10 @@ def ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, 
   p.dtype = dt
   p.causal = int(causal)
   p.softmax_scale = float(softmax_scale)
-  nbytes = int(_lib.ffpa_b200_bwd_workspace_bytes(p.batch, p.heads_q, p.heads_kv, p.seqlen_q,
-                                                   p.seqlen_kv, p.head_dim))
+  # recommended size: includes the score stash of the 5-GEMM path for head dims 384..512; with
+  # ``min_workspace`` (O(N) memory) the three recompute kernels run instead
+  ws_fn = _lib.ffpa_b200_bwd_workspace_bytes_min if min_workspace else _lib.ffpa_b200_bwd_workspace_bytes
+  nbytes = int(ws_fn(p.batch, p.heads_q, p.heads_kv, p.seqlen_q, p.seqlen_kv, p.head_dim))
   ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=Q.device)
   p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
   _bias_keep, p.bias_kind, p.bias_stride, p.bias = _bias_fields(attn_bias, Q, K)
@@ -364,7 +369,7 @@ def ffpa_attn_varlen_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, cu_seqlen
   p.dtype = _dtype_code(Q)
   p.causal = int(causal)
   p.softmax_scale = float(softmax_scale)
-  nbytes = int(_lib.ffpa_b200_bwd_workspace_bytes(p.batch, p.heads_q, p.heads_kv, p.seqlen_q, p.seqlen_kv, p.head_dim))
+  nbytes = int(_lib.ffpa_b200_bwd_workspace_bytes_min(p.batch, p.heads_q, p.heads_kv, p.seqlen_q, p.seqlen_kv, p.head_dim))
   ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=Q.device)
   p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
   with torch.cuda.device(Q.device):

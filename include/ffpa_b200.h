@@ -139,8 +139,15 @@ uint64_t ffpa_b200_fwd_workspace_bytes(int32_t batch, int32_t heads_q, int32_t h
 
 /* replaces ffpa_attn_backward (/root/reference/csrc/cuffpa/ffpa_api.cc:242-263, a thrower there) */
 int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream);
+/* Scratch sizes of the backward. `_bytes` is the RECOMMENDED size: for head dims 384..512 it includes the
+ * two 16-bit [B, Hq, Nq_pad, Nk_pad] score buffers of the stash path (dQ kernel stores P / dS tiles, dK and
+ * dV run as plain GEMMs over them: 5 GEMM passes instead of 8). `_bytes_min` is the REQUIRED size; given
+ * less than the recommended size the three recompute kernels run instead (O(N) memory). The packed
+ * variable-length mode only ever needs the minimum. */
 uint64_t ffpa_b200_bwd_workspace_bytes(int32_t batch, int32_t heads_q, int32_t heads_kv,
                                        int32_t seqlen_q, int32_t seqlen_kv, int32_t head_dim);
+uint64_t ffpa_b200_bwd_workspace_bytes_min(int32_t batch, int32_t heads_q, int32_t heads_kv,
+                                           int32_t seqlen_q, int32_t seqlen_kv, int32_t head_dim);
 
 /* replaces set_cuda_backend_impl / get_cuda_backend_impl (ffpa_api.cc:272-282, backend.h:16-25) */
 int ffpa_b200_set_backend_impl(int32_t impl);

@@ -263,6 +263,64 @@ def test_backward_large_headdim_full_length_sampled_head():
     assert cos > 0.999, f"{name}: cosine {cos}"
 
 
+def _raw_backward(q, k, v, d_o, causal, min_workspace):
+  """forward + backward through the native binding, choosing the backward path by workspace size"""
+  import ffpa_attn
+  from ffpa_attn import _C
+  from ffpa_attn.cuda import _ffpa_attn_forward_cuda
+
+  scale = q.size(-1) ** -0.5
+  out, lse = _ffpa_attn_forward_cuda(q, k, v, None, None, 0, 1, int(causal), scale)
+  dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+  n0 = ffpa_attn._C.launch_count()
+  _C.ffpa_attn_backward(q, k, v, out, lse, d_o, dq, dk, dv, 0, int(causal), scale, min_workspace=min_workspace)
+  torch.cuda.synchronize()
+  return dq, dk, dv, ffpa_attn._C.launch_count() - n0
+
+
+@pytest.mark.parametrize("D", [384, 448, 512])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("shape", [(1, 4, 2, 300, 300), (2, 2, 2, 130, 700), (1, 3, 1, 1000, 1000), (1, 2, 2, 5, 257)])
+def test_backward_stash_path_matches_recompute_path_and_oracle(D, causal, shape):
+  """Head dims 384..512: the dQ kernel stashes P / dS tiles and dK / dV run as GEMMs over them
+  (csrc/ffpa_bwd_gemm_sm100.cuh, 3 launches after the preprocess); with the minimum workspace the three
+  recompute kernels run. Both must agree with each other and with the oracle (GQA, tails, odd tile counts,
+  bottom-right causal with Nkv > Nq)."""
+  B, Hq, Hkv, Nq, Nkv = shape
+  q, k, v, d_o = _mk(B, Hq, Hkv, Nq, Nkv, D, torch.bfloat16, seed=21)
+  sq, sk, sv, n_stash = _raw_backward(q, k, v, d_o, causal, False)
+  rq, rk, rv, n_rec = _raw_backward(q, k, v, d_o, causal, True)
+  assert n_stash == 4 and n_rec >= 4   # preprocess + dQ + 2 GEMMs  vs  preprocess + dQ + dK + dV (+ converts)
+  for a, b_, name in ((sq, rq, "dQ"), (sk, rk, "dK"), (sv, rv, "dV")):
+    assert torch.isfinite(a.float()).all(), name
+    err = (a.float() - b_.float()).abs().max().item()
+    assert err < 2e-2 * max(1.0, b_.float().abs().max().item()), f"{name}: stash vs recompute {err}"
+  wq, wk, wv, _ = orc.attention_bwd(q.cpu(), k.cpu(), v.cpu(), d_o.cpu(), causal=causal)
+  tol = 1e-1 if causal else 5e-2
+  _cmp(sq, wq, tol, "dQ")
+  _cmp(sk, wk, tol, "dK")
+  _cmp(sv, wv, tol, "dV")
+
+
+def test_backward_stash_path_with_bias_and_dropout():
+  """GENERAL variant of the stashing dQ kernel: P_drop (dropout applied) feeds dV, dS feeds dK."""
+  import ffpa_attn
+
+  B, H, Nq, Nkv, D = 1, 2, 200, 264, 512
+  q, k, v, d_o = _mk(B, H, H, Nq, Nkv, D, torch.float16, seed=22)
+  bias = torch.randn(B, 1, Nq, Nkv, generator=torch.Generator().manual_seed(5)).to(DEV).requires_grad_(True)
+  torch.cuda.manual_seed(99)
+  seed, offset = int(torch.cuda.initial_seed()), int(torch.cuda._get_rng_state_offset())
+  qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+  ffpa_attn.ffpa_attn_func(qg, kg, vg, attn_mask=bias, dropout_p=0.15).backward(d_o)
+  torch.cuda.synchronize()
+  rq, rk, rv, rds = orc.attention_bwd(q.cpu(), k.cpu(), v.cpu(), d_o.cpu(), bias=bias.detach().cpu().double().numpy(),
+                                      dropout_p=0.15, philox_seed=seed, philox_offset=offset)
+  for got, want, name in ((qg.grad, rq, "dQ"), (kg.grad, rk, "dK"), (vg.grad, rv, "dV")):
+    _cmp(got, want, 2e-2, name)
+  _cmp(bias.grad, rds.sum(axis=1, keepdims=True), 2e-2, "dBias")
+
+
 def test_backward_rejects_unsupported():
   import ffpa_attn
 

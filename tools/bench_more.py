@@ -21,6 +21,7 @@ CASES = [
   ("nonaligned_n8191_h8_d512", 1, 8, 8, 8191, 8191, 512, False),
   ("self_n16384_d512", 1, 32, 32, 16384, 16384, 512, False),
   ("d320", 1, 32, 32, 8192, 8192, 320, False),
+  ("d384", 1, 32, 32, 8192, 8192, 384, False),
   ("d256", 1, 32, 32, 8192, 8192, 256, False),
   ("d128", 1, 32, 32, 8192, 8192, 128, False),
   ("d768", 1, 32, 32, 8192, 8192, 768, False),
@@ -76,6 +77,18 @@ def main():
 
       ms_b = timeit(bwd, 5)
       rec.update({"bwd_ms": ms_b, "bwd_tflops": 2.5 * f / ms_b * 1e-9})
+      if 384 <= D <= 512:
+        # A/B: the same backward with the minimum workspace (three recompute kernels, O(N) memory)
+        from ffpa_attn import _C
+        from ffpa_attn.cuda import _ffpa_attn_forward_cuda
+
+        o2, lse2 = _ffpa_attn_forward_cuda(q, k, v, None, None, 0, 1, int(causal), D ** -0.5)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ms_r = timeit(lambda: _C.ffpa_attn_backward(q, k, v, o2, lse2, d_o, dq, dk, dv, 0, int(causal), D ** -0.5,
+                                                    min_workspace=True), 5)
+        ms_s = timeit(lambda: _C.ffpa_attn_backward(q, k, v, o2, lse2, d_o, dq, dk, dv, 0, int(causal), D ** -0.5), 5)
+        rec.update({"bwd_recompute_ms": ms_r, "bwd_recompute_tflops": 2.5 * f / ms_r * 1e-9,
+                    "bwd_stash_ms": ms_s, "bwd_stash_tflops": 2.5 * f / ms_s * 1e-9})
     if name.startswith("c4") or name in ("c2_self_d512", "c2_causal_d512", "d320"):
       be = ffpa_attn.CUDABackend(enable_fp8=True)
       ms8 = timeit(lambda: ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=be, **kw), 10)
