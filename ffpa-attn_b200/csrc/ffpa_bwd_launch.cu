@@ -10,8 +10,8 @@ namespace ffpa {
 namespace bwd {
 template <bool BF16>
 int dispatch_bwd_dtype(int nqk, int kind, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
-                       const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp, int nclusters,
-                       cudaStream_t stream);
+                       const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const BwdKernelParams& kp,
+                       int nclusters, cudaStream_t stream);
 template <bool BF16>
 int launch_preprocess(const ffpa_bwd_params& a, float* lse2, float* delta, int nq_pad, cudaStream_t stream);
 template <bool BF16>
@@ -20,9 +20,9 @@ int launch_bwd_gemm(const CUtensorMap& map_t, const CUtensorMap& map_b, const Bw
 extern template int launch_bwd_gemm<true>(const CUtensorMap&, const CUtensorMap&, const BwdGemmParams&, int, cudaStream_t);
 extern template int launch_bwd_gemm<false>(const CUtensorMap&, const CUtensorMap&, const BwdGemmParams&, int, cudaStream_t);
 extern template int dispatch_bwd_dtype<true>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                                             const CUtensorMap&, const CUtensorMap&, const BwdKernelParams&, int, cudaStream_t);
+                                             const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const BwdKernelParams&, int, cudaStream_t);
 extern template int dispatch_bwd_dtype<false>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                                              const CUtensorMap&, const CUtensorMap&, const BwdKernelParams&, int, cudaStream_t);
+                                              const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const BwdKernelParams&, int, cudaStream_t);
 extern template int launch_preprocess<true>(const ffpa_bwd_params&, float*, float*, int, cudaStream_t);
 extern template int launch_preprocess<false>(const ffpa_bwd_params&, float*, float*, int, cudaStream_t);
 }  // namespace bwd
@@ -161,6 +161,10 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   const int nk_pad = (Nkv + 255) / 256 * 256;
   void* stash_p = use_stash ? static_cast<uint8_t*>(a.workspace) + stash_at : nullptr;
   void* stash_ds = use_stash ? static_cast<uint8_t*>(a.workspace) + stash_at + stash_one : nullptr;
+  const int64_t sstr[3] = {(int64_t)Hq * nq_pad * nk_pad, (int64_t)nq_pad * nk_pad, (int64_t)nk_pad};
+  CUtensorMap st_store;   // [64 rows x 64 keys] boxes: what one CTA's T buffer holds per key half
+  if (use_stash && !make_map4(&st_store, stash_ds, sstr, B, Hq, nq_pad, nk_pad, 64, 64))
+    return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the backward stash store map");
   const int max_clusters = sm_count() / 2;
   const int off = Nkv - Nq;
   auto run = [&](int kind, void* out, const int64_t* ostride, int rows, int heads, float* acc32,
@@ -230,8 +234,9 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
       }
       kp.sched = get_schedule(cost.data(), kp.n_items, ncl, &kp.sched_stride, stream);
     }
-    int r = bf16 ? bwd::dispatch_bwd_dtype<true>(nqk, kind, a1, a2, b1, b2, b3, kp, ncl, stream)
-                 : bwd::dispatch_bwd_dtype<false>(nqk, kind, a1, a2, b1, b2, b3, kp, ncl, stream);
+    const CUtensorMap& st = (kind == 0 && use_stash) ? st_store : a1;   // dS store map (dQ kind, stash path)
+    int r = bf16 ? bwd::dispatch_bwd_dtype<true>(nqk, kind, a1, a2, b1, b2, b3, st, kp, ncl, stream)
+                 : bwd::dispatch_bwd_dtype<false>(nqk, kind, a1, a2, b1, b2, b3, st, kp, ncl, stream);
     if (r) return r;
     if (kp.out32 != nullptr) {
       const int64_t total_vec = (int64_t)B * heads * rows * D / 8;
@@ -247,7 +252,6 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   if ((rc = run(0, a.dq, a.dq_stride, Nq, Hq, nullptr, q_km, do_km, k_km, v_km, k_mn))) return rc;
   if (use_stash) {
     CUtensorMap st_p, st_ds;
-    const int64_t sstr[3] = {(int64_t)Hq * nq_pad * nk_pad, (int64_t)nq_pad * nk_pad, (int64_t)nk_pad};
     if (!make_map4(&st_p, stash_p, sstr, B, Hq, nq_pad, nk_pad, 64, 128) ||
         !make_map4(&st_ds, stash_ds, sstr, B, Hq, nq_pad, nk_pad, 64, 128))
       return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the backward stash");

@@ -32,7 +32,8 @@ namespace bwd {
 constexpr int kSoftmaxWarps = 8;
 constexpr int kMmaWarp = 8;
 constexpr int kTmaWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kStoreWarp = 10;   // stash path: TMA-stores the dS tiles from shared memory (dQ kind)
+constexpr int kThreads = 352;
 constexpr int kSmemLimit = 232448;
 
 constexpr int kKindDQ = 0;
@@ -75,6 +76,7 @@ struct Barriers {
   uint64_t r_full[12], r_empty[12];
   uint64_t s_full[2];
   uint64_t t_full[2], t_empty[2];
+  uint64_t t_written[2], t_stored[2];   // stash path: T tile complete in this CTA / drained by the store warp
 };
 
 __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr) {
@@ -170,7 +172,8 @@ template <int NQK, bool BF16, int KIND, bool GENERAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
-                const __grid_constant__ CUtensorMap map_b3, const BwdKernelParams p) {
+                const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ CUtensorMap map_st,
+                const BwdKernelParams p) {
   using Cfg = BwdCfg<NQK, KIND>;
   constexpr int CG = 2;
   constexpr bool HAS_DP = Cfg::HAS_DP;
@@ -199,6 +202,8 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       ptx::mbar_init(bar(bars.s_full[i]), 1);
       ptx::mbar_init(bar(bars.t_full[i]), 2 * kSoftmaxWarps);
       ptx::mbar_init(bar(bars.t_empty[i]), 1);
+      ptx::mbar_init(bar(bars.t_written[i]), kSoftmaxWarps);
+      ptx::mbar_init(bar(bars.t_stored[i]), 1);
     }
     ptx::fence_mbar_init();
   }
@@ -413,6 +418,34 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       }
     }
     __syncwarp();
+  } else if (warp == kStoreWarp) {
+    // =========================================== stash store warp (dQ kind) =====================
+    // The dS tile the elementwise warps wrote for the MMA ([64 rows x 128 keys] of this CTA, two SW128 boxes)
+    // goes to the stash with TMA stores straight from shared memory: no register traffic, no LSU work.
+    if (KIND == kKindDQ && p.stash_ds != nullptr && ptx::elect_one()) {
+      ptx::prefetch_tmap(&map_st);
+      uint32_t g = 0;
+      for (uint32_t kidx = 0;; ++kidx) {
+        const int item_s = next_item(p, cluster, nclusters, kidx);
+        if (item_s < 0) break;
+        const Item itm = decode_item<KIND>(p, item_s, n_inner);
+        if (itm.n <= 0) continue;
+        const int hs = itm.bh % heads_it, b = itm.bh / heads_it;
+        const int q0 = itm.rt * 128 + 64 * (int)rank;
+        for (int i = 0; i < itm.n; ++i, ++g) {
+          const uint32_t sbuf = g & 1;
+          const int ci = itm.tr.first + (itm.s0 + i) % itm.tr.count;
+          ptx::mbar_wait(bar(bars.t_written[sbuf]), (g >> 1) & 1);
+          ptx::tma_store_4d(&map_st, sT + sbuf * 16384, ci * 128, q0, hs, b);
+          ptx::tma_store_4d(&map_st, sT + sbuf * 16384 + 8192, ci * 128 + 64, q0, hs, b);
+          ptx::bulk_commit_group();
+          ptx::bulk_wait_group_read0();
+          ptx::mbar_arrive(bar(bars.t_stored[sbuf]));
+        }
+      }
+      ptx::bulk_wait_group0();
+    }
+    __syncwarp();
   } else {
     // =========================================== elementwise warps + epilogue ===================
     const uint32_t t = threadIdx.x;
@@ -487,7 +520,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           if (p.causal) lim_lo = grow - off;
         }
         uint32_t pk[16];
-        uint32_t pp[4];   // stash path: packed P_drop of the current group of 8 columns
+        uint32_t pp[16];  // stash path: packed P_drop, stored to global after the tile has been handed to the MMA
         const bool stash = (KIND == kKindDQ) && p.stash_ds != nullptr;
         // GENERAL: additive bias, Philox dropout replay, dBias output (dQ kind). Query / key of
         // element jj: dQ kind (q = grow, key = col), dK/dV kinds (q = col, key = grow).
@@ -550,17 +583,10 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             }
           }
           pk[j >> 1] = BF16 ? ptx::pack_bf16x2(e[0], e[1]) : ptx::pack_f16x2(e[0], e[1]);
-          if (KIND == kKindDQ) {
-            pp[(j >> 1) & 3] = BF16 ? ptx::pack_bf16x2(pv[0], pv[1]) : ptx::pack_f16x2(pv[0], pv[1]);
-            if (stash && (j & 6) == 6) {   // 8 columns complete: one 16-byte store each for P_drop and dS
-              const int64_t so = stash_off + (j - 6);
-              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.stash_p) + so) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.stash_ds) + so) =
-                  make_uint4(pk[(j >> 1) - 3], pk[(j >> 1) - 2], pk[(j >> 1) - 1], pk[j >> 1]);
-            }
-          }
+          if (KIND == kKindDQ) pp[j >> 1] = BF16 ? ptx::pack_bf16x2(pv[0], pv[1]) : ptx::pack_f16x2(pv[0], pv[1]);
         }
         ptx::mbar_wait(bar(bars.t_empty[sbuf]), ((g >> 1) & 1) ^ 1);
+        if (stash) ptx::mbar_wait(bar(bars.t_stored[sbuf]), ((g >> 1) & 1) ^ 1);   // store warp has drained the buffer
         {
           const uint32_t prow = sT + sbuf * 16384 + kh * 8192 + row * 128;
 #pragma unroll
@@ -574,7 +600,17 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
-        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(sbuf ? l_t_full1 : l_t_full0);
+        if (ptx::lane_id() == 0) {
+          ptx::mbar_arrive_cluster(sbuf ? l_t_full1 : l_t_full0);
+          if (stash) ptx::mbar_arrive(bar(bars.t_written[sbuf]));
+        }
+        if (stash) {
+          // P_drop tile -> stash, issued after the hand-off so the stores (32 sectors per instruction: one row
+          // per lane) drain while this warp waits for the next S instead of stalling the S -> dS critical path
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.stash_p) + stash_off);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dst[c] = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+        }
       }
       // ---------------- epilogue: ACC (x scale) -> global ----------------
       {
@@ -688,7 +724,7 @@ __global__ void bwd_preprocess_kernel(const void* __restrict__ o, const void* __
 
 template <int NQK, bool BF16, int KIND, bool GENERAL>
 static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
-                              const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp,
+                              const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const BwdKernelParams& kp,
                               int nclusters, cudaStream_t stream) {
   using Cfg = BwdCfg<NQK, KIND>;
   auto kern = ffpa_bwd_kernel<NQK, BF16, KIND, GENERAL>;
@@ -702,7 +738,7 @@ static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, cons
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(bwd smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
     attr_set[dev_id] = true;
   }
-  kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(a1, a2, b1, b2, b3, kp);
+  kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(a1, a2, b1, b2, b3, st, kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "backward launch failed: %s", cudaGetErrorString(e));
   count_launch();
@@ -711,22 +747,22 @@ static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, cons
 
 template <bool BF16, int KIND, bool GENERAL>
 static int dispatch_bwd_nqk(int nqk, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
-                            const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp,
+                            const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const BwdKernelParams& kp,
                             int nclusters, cudaStream_t stream) {
   switch (nqk) {
-    case 1: return launch_bwd_variant<1, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 2: return launch_bwd_variant<2, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 3: return launch_bwd_variant<3, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 4: return launch_bwd_variant<4, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 5: return launch_bwd_variant<5, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 6: return launch_bwd_variant<6, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 7: return launch_bwd_variant<7, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 8: return launch_bwd_variant<8, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 1: return launch_bwd_variant<1, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 2: return launch_bwd_variant<2, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 3: return launch_bwd_variant<3, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 4: return launch_bwd_variant<4, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 5: return launch_bwd_variant<5, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 6: return launch_bwd_variant<6, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 7: return launch_bwd_variant<7, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 8: return launch_bwd_variant<8, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
     // head_dim > 512: the launcher rounds the box count up to an even number (TMA zero fill)
-    case 10: return launch_bwd_variant<10, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 12: return launch_bwd_variant<12, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 14: return launch_bwd_variant<14, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
-    case 16: return launch_bwd_variant<16, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, kp, nclusters, stream);
+    case 10: return launch_bwd_variant<10, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 12: return launch_bwd_variant<12, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 14: return launch_bwd_variant<14, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 16: return launch_bwd_variant<16, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
     default: return set_error(FFPA_ERR_UNSUPPORTED, "backward supports head_dim <= 1024");
   }
 }
@@ -734,17 +770,17 @@ static int dispatch_bwd_nqk(int nqk, const CUtensorMap& a1, const CUtensorMap& a
 // kind: 0 dQ, 1 dK, 2 dV
 template <bool BF16>
 int dispatch_bwd_dtype(int nqk, int kind, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
-                       const CUtensorMap& b2, const CUtensorMap& b3, const BwdKernelParams& kp, int nclusters,
+                       const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const BwdKernelParams& kp, int nclusters,
                        cudaStream_t stream) {
   const bool general = kp.bias_kind != 0 || kp.dropout_p > 0.f || kp.dbias != nullptr;
   if (general) {
-    if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, true>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
-    if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, true>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
-    return dispatch_bwd_nqk<BF16, kKindDV, true>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+    if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, true>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, true>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    return dispatch_bwd_nqk<BF16, kKindDV, true>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
   }
-  if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, false>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
-  if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, false>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
-  return dispatch_bwd_nqk<BF16, kKindDV, false>(nqk, a1, a2, b1, b2, b3, kp, nclusters, stream);
+  if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, false>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+  if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, false>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+  return dispatch_bwd_nqk<BF16, kKindDV, false>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
 }
 
 template <bool BF16>
