@@ -5,7 +5,8 @@
 // (the reference's SM100 backend pays the same, /root/reference/src/ffpa_attn/cute/_ffpa_bwd_sm100.py:301-484).
 // At large head dims a GEMM pass costs far more than moving an [Nq x Nkv] 16-bit tile through HBM, so the dQ
 // kernel (which owns S, dP, P and dS anyway) stashes P_drop and dS as 16-bit tiles
-//     stash[b, hq, q, k]   ([B, Hq, Nq_pad, Nk_pad], k contiguous; exactly the values its own MMA consumes)
+//     stash[b * Hq + hq][q tile][64-key block][128 q][64 k]   (tile-major: every TMA box is one contiguous
+//                                                              8-16 KB run; exactly the values its own MMA consumes)
 // and this kernel computes
 //     dV[keys, d] = sum_{heads of the group} sum_q P^T[keys, q]  dO[q, d]
 //     dK[keys, d] = scale * sum_{...}        sum_q dS^T[keys, q] Q[q, d]
@@ -106,6 +107,7 @@ ffpa_bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_t, const __grid_con
     if (ptx::elect_one()) {
       uint32_t rc = 0;
       uint32_t b_bytes = 0;
+      const uint64_t pol = ptx::l2_policy_evict_first();   // stash tiles are read exactly once
       for (int s = 0; s < n_slices; ++s) b_bytes += (slice_n(s) / 128) * 16384;
       for (uint32_t kidx = 0;; ++kidx) {
         const int item_s = next_gemm_item(p, cluster, nclusters, kidx);
@@ -120,9 +122,11 @@ ffpa_bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_t, const __grid_con
           ptx::mbar_wait(bar(bars.empty[stage]), (n & 1) ^ 1);
           if (rank == 0) ptx::mbar_expect_tx(bar(bars.full[stage]), 2 * (kGemmABytes + b_bytes));
           const uint32_t l_full = ptx::mapa(bar(bars.full[stage]), 0);
-          // A: stash tile, this CTA's 128 keys as two 64-key boxes of 128 query rows
-          ptx::tma_load_4d_2sm(sA(stage), &map_t, l_full, key0, ci * 128, hq, b);
-          ptx::tma_load_4d_2sm(sA(stage) + 16384, &map_t, l_full, key0 + 64, ci * 128, hq, b);
+          // A: stash tile, this CTA's 128 keys as two 64-key boxes of 128 query rows (each box is one
+          // contiguous 16 KB block of the tile-major stash: [b * Hq + h][query tile][64-key block][128][64])
+          const int blk = ci * (p.nk_pad >> 6) + (key0 >> 6), bhq = b * p.heads_q + hq;
+          ptx::tma_load_4d_2sm_hint(sA(stage), &map_t, l_full, 0, 0, blk, bhq, pol);
+          ptx::tma_load_4d_2sm_hint(sA(stage) + 16384, &map_t, l_full, 0, 0, blk + 1, bhq, pol);
           // B: dO / Q rows of the query tile, this CTA's half of every N slice as 64-wide boxes
           for (int s = 0; s < n_slices; ++s) {
             const int ns = slice_n(s), nb = ns / 128;

@@ -10,8 +10,8 @@ namespace ffpa {
 namespace bwd {
 template <bool BF16>
 int dispatch_bwd_dtype(int nqk, int kind, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
-                       const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const BwdKernelParams& kp,
-                       int nclusters, cudaStream_t stream);
+                       const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const CUtensorMap& sp,
+                       const BwdKernelParams& kp, int nclusters, cudaStream_t stream);
 template <bool BF16>
 int launch_preprocess(const ffpa_bwd_params& a, float* lse2, float* delta, int nq_pad, cudaStream_t stream);
 template <bool BF16>
@@ -20,9 +20,9 @@ int launch_bwd_gemm(const CUtensorMap& map_t, const CUtensorMap& map_b, const Bw
 extern template int launch_bwd_gemm<true>(const CUtensorMap&, const CUtensorMap&, const BwdGemmParams&, int, cudaStream_t);
 extern template int launch_bwd_gemm<false>(const CUtensorMap&, const CUtensorMap&, const BwdGemmParams&, int, cudaStream_t);
 extern template int dispatch_bwd_dtype<true>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                                             const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const BwdKernelParams&, int, cudaStream_t);
+                                             const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const BwdKernelParams&, int, cudaStream_t);
 extern template int dispatch_bwd_dtype<false>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                                              const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const BwdKernelParams&, int, cudaStream_t);
+                                              const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const BwdKernelParams&, int, cudaStream_t);
 extern template int launch_preprocess<true>(const ffpa_bwd_params&, float*, float*, int, cudaStream_t);
 extern template int launch_preprocess<false>(const ffpa_bwd_params&, float*, float*, int, cudaStream_t);
 }  // namespace bwd
@@ -161,9 +161,13 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   const int nk_pad = (Nkv + 255) / 256 * 256;
   void* stash_p = use_stash ? static_cast<uint8_t*>(a.workspace) + stash_at : nullptr;
   void* stash_ds = use_stash ? static_cast<uint8_t*>(a.workspace) + stash_at + stash_one : nullptr;
-  const int64_t sstr[3] = {(int64_t)Hq * nq_pad * nk_pad, (int64_t)nq_pad * nk_pad, (int64_t)nk_pad};
-  CUtensorMap st_store;   // [64 rows x 64 keys] boxes: what one CTA's T buffer holds per key half
-  if (use_stash && !make_map4(&st_store, stash_ds, sstr, B, Hq, nq_pad, nk_pad, 64, 64))
+  // tile-major stash: [B * Hq][query tile][64-key block][128 queries][64 keys] as a 4-D tensor
+  // (64, 128, blocks, B * Hq); a [64 x 64] store box / [128 x 64] load box is one contiguous run
+  const int sblocks = (nq_pad / 128) * (nk_pad / 64);
+  const int64_t sstr[3] = {(int64_t)sblocks * 8192, 8192, 64};
+  CUtensorMap st_store, sp_store;   // [64 rows x 64 keys] boxes: what one CTA's T buffer holds per key half
+  if (use_stash && (!make_map4(&st_store, stash_ds, sstr, B * Hq, sblocks, 128, 64, 64, 64) ||
+                    !make_map4(&sp_store, stash_p, sstr, B * Hq, sblocks, 128, 64, 64, 64)))
     return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the backward stash store map");
   const int max_clusters = sm_count() / 2;
   const int off = Nkv - Nq;
@@ -234,9 +238,10 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
       }
       kp.sched = get_schedule(cost.data(), kp.n_items, ncl, &kp.sched_stride, stream);
     }
-    const CUtensorMap& st = (kind == 0 && use_stash) ? st_store : a1;   // dS store map (dQ kind, stash path)
-    int r = bf16 ? bwd::dispatch_bwd_dtype<true>(nqk, kind, a1, a2, b1, b2, b3, st, kp, ncl, stream)
-                 : bwd::dispatch_bwd_dtype<false>(nqk, kind, a1, a2, b1, b2, b3, st, kp, ncl, stream);
+    const CUtensorMap& st = (kind == 0 && use_stash) ? st_store : a1;   // dS / P store maps (dQ kind, stash path)
+    const CUtensorMap& sp = (kind == 0 && use_stash) ? sp_store : a1;
+    int r = bf16 ? bwd::dispatch_bwd_dtype<true>(nqk, kind, a1, a2, b1, b2, b3, st, sp, kp, ncl, stream)
+                 : bwd::dispatch_bwd_dtype<false>(nqk, kind, a1, a2, b1, b2, b3, st, sp, kp, ncl, stream);
     if (r) return r;
     if (kp.out32 != nullptr) {
       const int64_t total_vec = (int64_t)B * heads * rows * D / 8;
@@ -252,13 +257,14 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   if ((rc = run(0, a.dq, a.dq_stride, Nq, Hq, nullptr, q_km, do_km, k_km, v_km, k_mn))) return rc;
   if (use_stash) {
     CUtensorMap st_p, st_ds;
-    if (!make_map4(&st_p, stash_p, sstr, B, Hq, nq_pad, nk_pad, 64, 128) ||
-        !make_map4(&st_ds, stash_ds, sstr, B, Hq, nq_pad, nk_pad, 64, 128))
+    if (!make_map4(&st_p, stash_p, sstr, B * Hq, sblocks, 128, 64, 64, 128) ||
+        !make_map4(&st_ds, stash_ds, sstr, B * Hq, sblocks, 128, 64, 64, 128))
       return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the backward stash");
     bwd::BwdGemmParams gp{};
     gp.batch = B; gp.heads_q = Hq; gp.heads_kv = Hkv; gp.seqlen_q = Nq; gp.seqlen_kv = Nkv; gp.head_dim = D;
     gp.causal = a.causal;
     gp.n_kblocks = nk_pad / 256;
+    gp.nk_pad = nk_pad;
     gp.n_items = gp.n_kblocks * B * Hkv;
     const int ncl = gp.n_items < max_clusters ? gp.n_items : max_clusters;
     gp.sched = nullptr;

@@ -173,7 +173,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
                 const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ CUtensorMap map_st,
-                const BwdKernelParams p) {
+                const __grid_constant__ CUtensorMap map_sp, const BwdKernelParams p) {
   using Cfg = BwdCfg<NQK, KIND>;
   constexpr int CG = 2;
   constexpr bool HAS_DP = Cfg::HAS_DP;
@@ -320,6 +320,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
       constexpr uint32_t idesc_s = ptx::make_idesc(fmt, fmt, 0, 0, 128, 128);
       constexpr uint32_t idesc_acc = ptx::make_idesc(fmt, fmt, 0, 1, 128, 128);
       uint32_t rc = 0, it = 0, g = 0, gp = 0;
+      const bool stash_mode = (KIND == kKindDQ) && p.stash_ds != nullptr;
       auto gemm_kmajor = [&](uint32_t sA, uint32_t d_tmem) {
 #pragma unroll
         for (int ks = 0; ks < Cfg::KST; ++ks) {
@@ -375,8 +376,9 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             ++g;
           }
           if (step >= 1) {
-            const uint32_t tbuf = gp & 1;
-            ptx::mbar_wait_cluster(bar(bars.t_full[tbuf]), (gp >> 1) & 1);
+            // stash path: T is single-buffered (buffer 0; buffer 1 stages the P tile for its TMA store)
+            const uint32_t tbuf = stash_mode ? 0u : (gp & 1);
+            ptx::mbar_wait_cluster(bar(bars.t_full[tbuf]), (stash_mode ? gp : (gp >> 1)) & 1);
             ptx::tc_fence_after();
 #pragma unroll
             for (int s = 0; s < Cfg::NSL; ++s) {
@@ -424,6 +426,8 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     // goes to the stash with TMA stores straight from shared memory: no register traffic, no LSU work.
     if (KIND == kKindDQ && p.stash_ds != nullptr && ptx::elect_one()) {
       ptx::prefetch_tmap(&map_st);
+      ptx::prefetch_tmap(&map_sp);
+      const uint64_t pol = ptx::l2_policy_evict_first();   // written once, read once by the GEMM kernels: keep K/V in L2
       uint32_t g = 0;
       for (uint32_t kidx = 0;; ++kidx) {
         const int item_s = next_item(p, cluster, nclusters, kidx);
@@ -431,16 +435,20 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         const Item itm = decode_item<KIND>(p, item_s, n_inner);
         if (itm.n <= 0) continue;
         const int hs = itm.bh % heads_it, b = itm.bh / heads_it;
-        const int q0 = itm.rt * 128 + 64 * (int)rank;
         for (int i = 0; i < itm.n; ++i, ++g) {
-          const uint32_t sbuf = g & 1;
           const int ci = itm.tr.first + (itm.s0 + i) % itm.tr.count;
-          ptx::mbar_wait(bar(bars.t_written[sbuf]), (g >> 1) & 1);
-          ptx::tma_store_4d(&map_st, sT + sbuf * 16384, ci * 128, q0, hs, b);
-          ptx::tma_store_4d(&map_st, sT + sbuf * 16384 + 8192, ci * 128 + 64, q0, hs, b);
+          ptx::mbar_wait(bar(bars.t_written[0]), g & 1);
+          // stash layout: [b * Hq + h][query tile][64-key block][128 queries][64 keys] -- every box this CTA
+          // stores is one contiguous 8 KB run (row-major [Nq, Nk] scatters 128-byte pieces 2 Nk bytes apart,
+          // which caps the DRAM write rate near 1.2 TB/s and starves the operand loads)
+          const int blk = itm.rt * (p.nk_pad >> 6) + 2 * ci, bhq = b * p.heads_q + hs, qh = 64 * (int)rank;
+          ptx::tma_store_4d_hint(&map_st, sT, 0, qh, blk, bhq, pol);                        // dS (T buffer 0)
+          ptx::tma_store_4d_hint(&map_st, sT + 8192, 0, qh, blk + 1, bhq, pol);
+          ptx::tma_store_4d_hint(&map_sp, sT + 16384, 0, qh, blk, bhq, pol);               // P_drop (staging buffer)
+          ptx::tma_store_4d_hint(&map_sp, sT + 16384 + 8192, 0, qh, blk + 1, bhq, pol);
           ptx::bulk_commit_group();
           ptx::bulk_wait_group_read0();
-          ptx::mbar_arrive(bar(bars.t_stored[sbuf]));
+          ptx::mbar_arrive(bar(bars.t_stored[0]));
         }
       }
       ptx::bulk_wait_group0();
@@ -526,8 +534,6 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         // element jj: dQ kind (q = grow, key = col), dK/dV kinds (q = col, key = grow).
         const int hq_cur = (KIND == kKindDQ) ? hs : hs * group + gi;
         const float inv_keep = GENERAL ? 1.f / (1.f - p.dropout_p) : 1.f;
-        // stash row of this thread: [b, hq, grow, col0 ..] (16-bit elements; col0 is a multiple of 32)
-        const int64_t stash_off = stash ? ((((int64_t)b * p.heads_q + hq_cur) * p.nq_pad + grow) * (int64_t)p.nk_pad + col0) : 0;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float e[2], pv[2] = {0.f, 0.f};
@@ -585,10 +591,22 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
           pk[j >> 1] = BF16 ? ptx::pack_bf16x2(e[0], e[1]) : ptx::pack_f16x2(e[0], e[1]);
           if (KIND == kKindDQ) pp[j >> 1] = BF16 ? ptx::pack_bf16x2(pv[0], pv[1]) : ptx::pack_f16x2(pv[0], pv[1]);
         }
-        ptx::mbar_wait(bar(bars.t_empty[sbuf]), ((g >> 1) & 1) ^ 1);
-        if (stash) ptx::mbar_wait(bar(bars.t_stored[sbuf]), ((g >> 1) & 1) ^ 1);   // store warp has drained the buffer
+        // stash path: T single-buffered (buffer 0), buffer 1 stages P_drop; both leave through the store warp
+        const uint32_t tb = stash ? 0u : sbuf;
+        ptx::mbar_wait(bar(bars.t_empty[tb]), ((stash ? g : (g >> 1)) & 1) ^ 1);
+        if (stash) {
+          ptx::mbar_wait(bar(bars.t_stored[0]), (g & 1) ^ 1);   // store warp has drained both buffers
+          const uint32_t prow = sT + 16384 + kh * 8192 + row * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = prow + (((4 * ch + c) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pp[4 * c]),
+                         "r"(pp[4 * c + 1]), "r"(pp[4 * c + 2]), "r"(pp[4 * c + 3])
+                         : "memory");
+          }
+        }
         {
-          const uint32_t prow = sT + sbuf * 16384 + kh * 8192 + row * 128;
+          const uint32_t prow = sT + tb * 16384 + kh * 8192 + row * 128;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint32_t addr = prow + (((4 * ch + c) ^ (row & 7)) << 4);
@@ -601,21 +619,15 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         ptx::tc_fence_before();
         __syncwarp();
         if (ptx::lane_id() == 0) {
-          ptx::mbar_arrive_cluster(sbuf ? l_t_full1 : l_t_full0);
-          if (stash) ptx::mbar_arrive(bar(bars.t_written[sbuf]));
-        }
-        if (stash) {
-          // P_drop tile -> stash, issued after the hand-off so the stores (32 sectors per instruction: one row
-          // per lane) drain while this warp waits for the next S instead of stalling the S -> dS critical path
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.stash_p) + stash_off);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) dst[c] = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+          ptx::mbar_arrive_cluster(tb ? l_t_full1 : l_t_full0);
+          if (stash) ptx::mbar_arrive(bar(bars.t_written[0]));
         }
       }
       // ---------------- epilogue: ACC (x scale) -> global ----------------
       {
         const uint32_t gl = g - 1;
-        ptx::mbar_wait(bar(bars.t_empty[gl & 1]), (gl >> 1) & 1);
+        const bool stash_e = (KIND == kKindDQ) && p.stash_ds != nullptr;
+        ptx::mbar_wait(bar(bars.t_empty[stash_e ? 0u : (gl & 1)]), (stash_e ? gl : (gl >> 1)) & 1);
         ptx::tc_fence_after();
         const float mulo = (KIND == kKindDV) ? 1.f : p.scale;
 #pragma unroll
@@ -724,7 +736,7 @@ __global__ void bwd_preprocess_kernel(const void* __restrict__ o, const void* __
 
 template <int NQK, bool BF16, int KIND, bool GENERAL>
 static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
-                              const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const BwdKernelParams& kp,
+                              const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const CUtensorMap& sp, const BwdKernelParams& kp,
                               int nclusters, cudaStream_t stream) {
   using Cfg = BwdCfg<NQK, KIND>;
   auto kern = ffpa_bwd_kernel<NQK, BF16, KIND, GENERAL>;
@@ -738,7 +750,7 @@ static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, cons
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(bwd smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
     attr_set[dev_id] = true;
   }
-  kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(a1, a2, b1, b2, b3, st, kp);
+  kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(a1, a2, b1, b2, b3, st, sp, kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "backward launch failed: %s", cudaGetErrorString(e));
   count_launch();
@@ -747,22 +759,22 @@ static int launch_bwd_variant(const CUtensorMap& a1, const CUtensorMap& a2, cons
 
 template <bool BF16, int KIND, bool GENERAL>
 static int dispatch_bwd_nqk(int nqk, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
-                            const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const BwdKernelParams& kp,
+                            const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const CUtensorMap& sp, const BwdKernelParams& kp,
                             int nclusters, cudaStream_t stream) {
   switch (nqk) {
-    case 1: return launch_bwd_variant<1, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 2: return launch_bwd_variant<2, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 3: return launch_bwd_variant<3, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 4: return launch_bwd_variant<4, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 5: return launch_bwd_variant<5, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 6: return launch_bwd_variant<6, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 7: return launch_bwd_variant<7, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 8: return launch_bwd_variant<8, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 1: return launch_bwd_variant<1, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 2: return launch_bwd_variant<2, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 3: return launch_bwd_variant<3, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 4: return launch_bwd_variant<4, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 5: return launch_bwd_variant<5, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 6: return launch_bwd_variant<6, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 7: return launch_bwd_variant<7, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 8: return launch_bwd_variant<8, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
     // head_dim > 512: the launcher rounds the box count up to an even number (TMA zero fill)
-    case 10: return launch_bwd_variant<10, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 12: return launch_bwd_variant<12, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 14: return launch_bwd_variant<14, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    case 16: return launch_bwd_variant<16, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    case 10: return launch_bwd_variant<10, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 12: return launch_bwd_variant<12, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 14: return launch_bwd_variant<14, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    case 16: return launch_bwd_variant<16, BF16, KIND, GENERAL>(a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
     default: return set_error(FFPA_ERR_UNSUPPORTED, "backward supports head_dim <= 1024");
   }
 }
@@ -770,17 +782,17 @@ static int dispatch_bwd_nqk(int nqk, const CUtensorMap& a1, const CUtensorMap& a
 // kind: 0 dQ, 1 dK, 2 dV
 template <bool BF16>
 int dispatch_bwd_dtype(int nqk, int kind, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b1,
-                       const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const BwdKernelParams& kp, int nclusters,
+                       const CUtensorMap& b2, const CUtensorMap& b3, const CUtensorMap& st, const CUtensorMap& sp, const BwdKernelParams& kp, int nclusters,
                        cudaStream_t stream) {
   const bool general = kp.bias_kind != 0 || kp.dropout_p > 0.f || kp.dbias != nullptr;
   if (general) {
-    if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, true>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, true>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-    return dispatch_bwd_nqk<BF16, kKindDV, true>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+    if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, true>(nqk, a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, true>(nqk, a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+    return dispatch_bwd_nqk<BF16, kKindDV, true>(nqk, a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
   }
-  if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, false>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-  if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, false>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
-  return dispatch_bwd_nqk<BF16, kKindDV, false>(nqk, a1, a2, b1, b2, b3, st, kp, nclusters, stream);
+  if (kind == kKindDQ) return dispatch_bwd_nqk<BF16, kKindDQ, false>(nqk, a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+  if (kind == kKindDK) return dispatch_bwd_nqk<BF16, kKindDK, false>(nqk, a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
+  return dispatch_bwd_nqk<BF16, kKindDV, false>(nqk, a1, a2, b1, b2, b3, st, sp, kp, nclusters, stream);
 }
 
 template <bool BF16>
