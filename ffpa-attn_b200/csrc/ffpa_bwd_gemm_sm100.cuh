@@ -38,12 +38,14 @@ struct GemmBarriers {
   uint64_t acc_full, acc_empty;
 };
 
-struct GemmItem { int kb, bh, first, count, T; };
+struct GemmItem { int kb, bh, pass, first, count, T; };
 
 __device__ __forceinline__ GemmItem decode_gemm_item(const BwdGemmParams& p, int item, int group) {
   GemmItem it;
   it.kb = item % p.n_kblocks;
-  it.bh = item / p.n_kblocks;
+  const int rest = item / p.n_kblocks;
+  it.pass = rest % p.n_pass;     // 512-wide output slab (head dims > 512: the accumulator is one TMEM)
+  it.bh = rest / p.n_pass;
   const int tq = (p.seqlen_q + 127) >> 7;
   int first = 0;
   if (p.causal) {
@@ -99,22 +101,24 @@ ffpa_bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_t, const __grid_con
 
   const int group = p.heads_q / p.heads_kv;
   const int D = p.head_dim;
-  const int n_slices = (D + 255) >> 8;                                   // N = 256 slices (the last may be 128)
-  auto slice_n = [&](int s) { return (D - 256 * s) > 128 ? 256 : 128; };
+  // output slab of pass `ps`: head dims [512 ps, 512 ps + w); N = 256 slices (the last may be 128)
+  auto slab_w = [&](int ps) { return (D - 512 * ps) > 512 ? 512 : (D - 512 * ps); };
+  auto slice_n = [&](int w, int s) { return (w - 256 * s) > 128 ? 256 : 128; };
 
   if (warp == 9) {
     // =========================================== TMA producer (both CTAs) =======================
     if (ptx::elect_one()) {
       uint32_t rc = 0;
-      uint32_t b_bytes = 0;
-      const uint64_t pol = ptx::l2_policy_evict_first();   // stash tiles are read exactly once
-      for (int s = 0; s < n_slices; ++s) b_bytes += (slice_n(s) / 128) * 16384;
+      const uint64_t pol = ptx::l2_policy_evict_first();   // stash tiles are read once (per slab pass)
       for (uint32_t kidx = 0;; ++kidx) {
         const int item_s = next_gemm_item(p, cluster, nclusters, kidx);
         if (item_s < 0) break;
         const GemmItem it = decode_gemm_item(p, item_s, group);
         const int hk = it.bh % p.heads_kv, b = it.bh / p.heads_kv;
         const int key0 = it.kb * 256 + 128 * (int)rank;
+        const int w = slab_w(it.pass), n_slices = (w + 255) >> 8, d_base = 512 * it.pass;
+        uint32_t b_bytes = 0;
+        for (int s = 0; s < n_slices; ++s) b_bytes += (slice_n(w, s) / 128) * 16384;
         for (int step = 0; step < it.T; ++step, ++rc) {
           const int gi = step / it.count, ci = it.first + step % it.count;
           const int hq = hk * group + gi;
@@ -129,10 +133,10 @@ ffpa_bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_t, const __grid_con
           ptx::tma_load_4d_2sm_hint(sA(stage) + 16384, &map_t, l_full, 0, 0, blk + 1, bhq, pol);
           // B: dO / Q rows of the query tile, this CTA's half of every N slice as 64-wide boxes
           for (int s = 0; s < n_slices; ++s) {
-            const int ns = slice_n(s), nb = ns / 128;
+            const int ns = slice_n(w, s), nb = ns / 128;
             for (int bx = 0; bx < nb; ++bx)
               ptx::tma_load_4d_2sm(sB(stage) + s * 32768 + bx * 16384, &map_b, l_full,
-                                   256 * s + (ns / 2) * (int)rank + 64 * bx, ci * 128, hq, b);
+                                   d_base + 256 * s + (ns / 2) * (int)rank + 64 * bx, ci * 128, hq, b);
           }
         }
       }
@@ -150,6 +154,7 @@ ffpa_bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_t, const __grid_con
         if (item_s < 0) break;
         const GemmItem it = decode_gemm_item(p, item_s, group);
         if (it.T <= 0) continue;
+        const int w = slab_w(it.pass), n_slices = (w + 255) >> 8;
         // accumulator free? (epilogue of the previous item has drained TMEM)
         ptx::mbar_wait_cluster(bar(bars.acc_empty), (itc & 1) ^ 1);
         ptx::tc_fence_after();
@@ -158,7 +163,7 @@ ffpa_bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_t, const __grid_con
           ptx::mbar_wait(bar(bars.full[stage]), n & 1);
           ptx::tc_fence_after();
           for (int s = 0; s < n_slices; ++s) {
-            const uint32_t idesc = slice_n(s) == 256 ? idesc256 : idesc128;
+            const uint32_t idesc = slice_n(w, s) == 256 ? idesc256 : idesc128;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {   // 16 queries per instruction
               const uint64_t ad = ptx::make_smem_desc_sw128(sA(stage) + kk * 2048, 16384, 1024);
@@ -188,21 +193,22 @@ ffpa_bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_t, const __grid_con
       const bool row_ok = key < p.seqlen_kv;
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
                       2 * ((int64_t)b * p.out_stride[0] + (int64_t)hk * p.out_stride[1] + (int64_t)key * p.out_stride[2]);
+      const int w = slab_w(it.pass), d_base = 512 * it.pass;
       if (it.T <= 0) {   // no query sees these keys: zero gradient
         if (row_ok)
-          for (int d = (int)wg * 8; d < D; d += 16) *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(0, 0, 0, 0);
+          for (int d = d_base + (int)wg * 8; d < d_base + w; d += 16) *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(0, 0, 0, 0);
         continue;
       }
       ptx::mbar_wait(bar(bars.acc_full), itc & 1);
       ptx::tc_fence_after();
-      for (int c0 = (int)wg * 32; c0 < D; c0 += 64) {
+      for (int c0 = (int)wg * 32; c0 < w; c0 += 64) {
         uint32_t r[32];
         ptx::tmem_ld_x32(tmem + lane_base + c0, r);
         ptx::tmem_wait_ld();
         if (row_ok) {
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            const int d = c0 + 8 * v;
+            const int d = d_base + c0 + 8 * v;
             if (d < D) {
               uint32_t w[4];
 #pragma unroll

@@ -49,11 +49,11 @@ static bool may_split_kv(int batch, int heads_kv, int seqlen_kv) {
 
 // Stash path (ffpa_bwd_gemm_sm100.cuh): bytes of ONE 16-bit [B, Hq, nq_pad, nk_pad] score buffer (two are
 // needed: P_drop and dS), or 0 when the path does not apply. It pays when a GEMM pass over the head dim costs
-// more than moving the N x N tile through HBM: head dims 384..512 (above, the accumulator of the GEMM-only
-// kernel no longer fits TMEM). FFPA_BWD_STASH=0 disables it, FFPA_BWD_STASH_MAX_GB (default 20) bounds both
+// more than moving the N x N tile through HBM: head dims >= 384 (above 512 the dQ kernel stores on the first
+// of its two slab passes and the GEMM-only kernel runs one pass per 512-wide output slab). FFPA_BWD_STASH=0 disables it, FFPA_BWD_STASH_MAX_GB (default 20) bounds both
 // buffers together; beyond the bound the three recompute kernels run.
 static uint64_t bwd_stash_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
-  if (head_dim < 384 || head_dim > 512) return 0;
+  if (head_dim < 384 || head_dim > 1024) return 0;
   static int enabled = -1;
   static double max_gb = 20.0;
   if (enabled < 0) {
@@ -265,7 +265,8 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
     gp.causal = a.causal;
     gp.n_kblocks = nk_pad / 256;
     gp.nk_pad = nk_pad;
-    gp.n_items = gp.n_kblocks * B * Hkv;
+    gp.n_pass = D > 512 ? 2 : 1;
+    gp.n_items = gp.n_kblocks * B * Hkv * gp.n_pass;
     const int ncl = gp.n_items < max_clusters ? gp.n_items : max_clusters;
     gp.sched = nullptr;
     gp.sched_stride = 0;

@@ -433,9 +433,9 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         const int item_s = next_item(p, cluster, nclusters, kidx);
         if (item_s < 0) break;
         const Item itm = decode_item<KIND>(p, item_s, n_inner);
-        if (itm.n <= 0) continue;
+        if (itm.n <= 0 || itm.pass != 0) continue;   // head dims > 512: the second slab pass recomputes, pass 0 stores
         const int hs = itm.bh % heads_it, b = itm.bh / heads_it;
-        for (int i = 0; i < itm.n; ++i, ++g) {
+        for (int i = 0; i < itm.n; ++i, ++g) {       // g counts stored tiles only
           const int ci = itm.tr.first + (itm.s0 + i) % itm.tr.count;
           ptx::mbar_wait(bar(bars.t_written[0]), g & 1);
           // stash layout: [b * Hq + h][query tile][64-key block][128 queries][64 keys] -- every box this CTA
@@ -464,7 +464,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
     const uint32_t lane_base = ((warp & 3) * 32u) << 16;
     const uint32_t l_t_full0 = ptx::mapa(bar(bars.t_full[0]), 0);
     const uint32_t l_t_full1 = ptx::mapa(bar(bars.t_full[1]), 0);
-    uint32_t g = 0;
+    uint32_t g = 0, gs = 0;   // tiles processed / tiles handed to the stash store warp
     for (uint32_t kidx = 0;; ++kidx) {
       const int item_s = next_item(p, cluster, nclusters, kidx);
       if (item_s < 0) break;
@@ -529,7 +529,8 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         }
         uint32_t pk[16];
         uint32_t pp[16];  // stash path: packed P_drop, stored to global after the tile has been handed to the MMA
-        const bool stash = (KIND == kKindDQ) && p.stash_ds != nullptr;
+        const bool stash = (KIND == kKindDQ) && p.stash_ds != nullptr;   // launch-wide: T single-buffered
+        const bool stash_w = stash && itm.pass == 0;                     // this item's tiles are stored
         // GENERAL: additive bias, Philox dropout replay, dBias output (dQ kind). Query / key of
         // element jj: dQ kind (q = grow, key = col), dK/dV kinds (q = col, key = grow).
         const int hq_cur = (KIND == kKindDQ) ? hs : hs * group + gi;
@@ -594,8 +595,9 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         // stash path: T single-buffered (buffer 0), buffer 1 stages P_drop; both leave through the store warp
         const uint32_t tb = stash ? 0u : sbuf;
         ptx::mbar_wait(bar(bars.t_empty[tb]), ((stash ? g : (g >> 1)) & 1) ^ 1);
-        if (stash) {
-          ptx::mbar_wait(bar(bars.t_stored[0]), (g & 1) ^ 1);   // store warp has drained both buffers
+        // store warp has drained both buffers of the most recent stored tile (gs = tiles stored so far)
+        if (stash && gs > 0) ptx::mbar_wait(bar(bars.t_stored[0]), (gs - 1) & 1);
+        if (stash_w) {
           const uint32_t prow = sT + 16384 + kh * 8192 + row * 128;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -620,8 +622,9 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         __syncwarp();
         if (ptx::lane_id() == 0) {
           ptx::mbar_arrive_cluster(tb ? l_t_full1 : l_t_full0);
-          if (stash) ptx::mbar_arrive(bar(bars.t_written[0]));
+          if (stash_w) ptx::mbar_arrive(bar(bars.t_written[0]));
         }
+        if (stash_w) ++gs;
       }
       // ---------------- epilogue: ACC (x scale) -> global ----------------
       {

@@ -79,6 +79,7 @@ struct BwdGemmParams {
   float mul;               // softmax_scale for dK, 1 for dV
   int n_kblocks, n_items;  // 256-key blocks per (b, kv head); items = n_kblocks * B * Hkv
   int nk_pad;              // padded key count of the stash (multiple of 256)
+  int n_pass;              // 512-wide output slabs per item (2 when head_dim > 512)
   const int* sched;
   int sched_stride;
 };

@@ -278,11 +278,11 @@ def _raw_backward(q, k, v, d_o, causal, min_workspace):
   return dq, dk, dv, ffpa_attn._C.launch_count() - n0
 
 
-@pytest.mark.parametrize("D", [384, 448, 512])
+@pytest.mark.parametrize("D", [384, 448, 512, 520, 640, 1024])
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("shape", [(1, 4, 2, 300, 300), (2, 2, 2, 130, 700), (1, 3, 1, 1000, 1000), (1, 2, 2, 5, 257)])
 def test_backward_stash_path_matches_recompute_path_and_oracle(D, causal, shape):
-  """Head dims 384..512: the dQ kernel stashes P / dS tiles and dK / dV run as GEMMs over them
+  """Head dims 384..1024: the dQ kernel stashes P / dS tiles (on the first slab pass when D > 512) and dK / dV run as GEMMs over them
   (csrc/ffpa_bwd_gemm_sm100.cuh, 3 launches after the preprocess); with the minimum workspace the three
   recompute kernels run. Both must agree with each other and with the oracle (GQA, tails, odd tile counts,
   bottom-right causal with Nkv > Nq)."""

@@ -77,7 +77,7 @@ def main():
 
       ms_b = timeit(bwd, 5)
       rec.update({"bwd_ms": ms_b, "bwd_tflops": 2.5 * f / ms_b * 1e-9})
-      if 384 <= D <= 512:
+      if 384 <= D <= 1024:
         # A/B: the same backward with the minimum workspace (three recompute kernels, O(N) memory)
         from ffpa_attn import _C
         from ffpa_attn.cuda import _ffpa_attn_forward_cuda
