@@ -47,26 +47,35 @@ static bool may_split_kv(int batch, int heads_kv, int seqlen_kv) {
   return kv_items < 8ll * (sm_count() / 2);
 }
 
-// Stash path (ffpa_bwd_gemm_sm100.cuh): bytes of ONE 16-bit [B, Hq, nq_pad, nk_pad] score buffer (two are
-// needed: P_drop and dS), or 0 when the path does not apply. It pays when a GEMM pass over the head dim costs
-// more than moving the N x N tile through HBM: head dims >= 384 (above 512 the dQ kernel stores on the first
-// of its two slab passes and the GEMM-only kernel runs one pass per 512-wide output slab). FFPA_BWD_STASH=0 disables it, FFPA_BWD_STASH_MAX_GB (default 20) bounds both
-// buffers together; beyond the bound the three recompute kernels run.
-static uint64_t bwd_stash_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
-  if (head_dim < 384 || head_dim > 1024) return 0;
-  static int enabled = -1;
-  static double max_gb = 20.0;
-  if (enabled < 0) {
-    const char* e = getenv("FFPA_BWD_STASH");
-    enabled = (e && e[0] == '0') ? 0 : 1;
-    const char* g = getenv("FFPA_BWD_STASH_MAX_GB");
-    if (g) max_gb = atof(g);
-  }
-  if (!enabled) return 0;
+// Stash path (ffpa_bwd_gemm_sm100.cuh): two 16-bit [B, Hq, nq_pad, nk_pad] score buffers (P_drop and dS).
+// It pays when a GEMM pass over the head dim costs more than moving the N x N tile through HBM: head dims
+// >= 384 (above 512 the dQ kernel stores on the first of its two slab passes and the GEMM-only kernel runs one
+// pass per 512-wide output slab). FFPA_BWD_STASH=0 disables it; FFPA_BWD_STASH_MAX_GB (default 20) bounds both
+// buffers together: a larger problem is cut into (batch element, KV-head range) chunks that run one after the
+// other through the same buffers; if not even one KV head fits, the three recompute kernels run (O(N) memory).
+struct StashPlan {
+  uint64_t one = 0;     // bytes of ONE score buffer (of a chunk when chunked); 0 = path does not apply
+  int chunk_hkv = 0;    // KV heads per chunk
+  bool chunked = false;
+};
+static StashPlan stash_plan(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
+  StashPlan pl;
+  if (head_dim < 384 || head_dim > 1024 || heads_kv <= 0) return pl;
+  const char* e = getenv("FFPA_BWD_STASH");
+  if (e && e[0] == '0') return pl;
+  const char* g = getenv("FFPA_BWD_STASH_MAX_GB");
+  const double cap = (g ? atof(g) : 20.0) * 1073741824.0;
   const uint64_t nq_pad = ((uint64_t)seqlen_q + 127) / 128 * 128, nk_pad = ((uint64_t)seqlen_kv + 255) / 256 * 256;
-  const uint64_t one = align256((uint64_t)batch * heads_q * nq_pad * nk_pad * 2);
-  if (2.0 * (double)one > max_gb * 1073741824.0) return 0;
-  return one;
+  const int group = heads_q / heads_kv;
+  const uint64_t per_hkv = (uint64_t)group * nq_pad * nk_pad * 2;   // multiple of 256 bytes
+  const uint64_t total = (uint64_t)batch * heads_kv * per_hkv;
+  if (2.0 * (double)total <= cap) { pl.one = total; pl.chunk_hkv = heads_kv; return pl; }
+  int hc = (int)(cap / (2.0 * (double)per_hkv));
+  hc = hc > heads_kv ? heads_kv : hc;
+  // a chunk must still fill the machine: query row tiles x query heads of the chunk
+  if (hc < 1 || (int64_t)hc * group * (int64_t)(nq_pad / 128) < sm_count() / 2) return pl;
+  pl.one = (uint64_t)hc * per_hkv; pl.chunk_hkv = hc; pl.chunked = true;
+  return pl;
 }
 
 uint64_t bwd_workspace_bytes_min(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
@@ -78,8 +87,14 @@ uint64_t bwd_workspace_bytes_min(int batch, int heads_q, int heads_kv, int seqle
 }
 
 uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
-  return bwd_workspace_bytes_min(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim) +
-         2 * bwd_stash_bytes(batch, heads_q, seqlen_q, seqlen_kv, head_dim);
+  const uint64_t whole = bwd_workspace_bytes_min(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
+  const StashPlan pl = stash_plan(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
+  if (pl.one == 0) return whole;
+  if (!pl.chunked) return whole + 2 * pl.one;
+  // chunked: every chunk is a self-contained sub-problem (batch 1, chunk_hkv KV heads) in the same scratch
+  const int group = heads_q / heads_kv;
+  const uint64_t sub = bwd_workspace_bytes_min(1, pl.chunk_hkv * group, pl.chunk_hkv, seqlen_q, seqlen_kv, head_dim) + 2 * pl.one;
+  return sub > whole ? sub : whole;
 }
 
 template <bool BF16>
@@ -108,6 +123,34 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   const int nqk = D > 512 ? (D + 127) / 128 * 2 : (D + 63) / 64;
   const int n_pass = D > 512 ? 2 : 1;
   const int nq_pad = (a.seqlen_q + 127) / 128 * 128;
+  const StashPlan plan = a.cu_seqlens_q ? StashPlan{} : stash_plan(a.batch, a.heads_q, a.heads_kv, a.seqlen_q, a.seqlen_kv, D);
+  if (plan.chunked && a.bias_kind == FFPA_BIAS_NONE && !(a.dropout_p > 0.f) && a.d_bias == nullptr) {
+    // stash buffers bounded by FFPA_BWD_STASH_MAX_GB: run (batch element, KV-head range) chunks one after the other
+    // through the same scratch (stream order serialises them); each chunk is an ordinary dense sub-problem
+    const int group = a.heads_q / a.heads_kv;
+    const uint64_t sub_need = bwd_workspace_bytes_min(1, plan.chunk_hkv * group, plan.chunk_hkv, a.seqlen_q, a.seqlen_kv, D) + 2 * plan.one;
+    if (a.workspace && a.workspace_bytes >= sub_need) {
+      auto off = [](const void* p, int64_t elems) { return static_cast<const void*>(static_cast<const uint8_t*>(p) + 2 * elems); };
+      for (int b = 0; b < a.batch; ++b)
+        for (int hk0 = 0; hk0 < a.heads_kv; hk0 += plan.chunk_hkv) {
+          const int hc = (a.heads_kv - hk0) < plan.chunk_hkv ? (a.heads_kv - hk0) : plan.chunk_hkv;
+          const int hq0 = hk0 * group;
+          ffpa_bwd_params s = a;
+          s.batch = 1; s.heads_kv = hc; s.heads_q = hc * group;
+          s.q = off(a.q, b * a.q_stride[0] + hq0 * a.q_stride[1]);
+          s.o = off(a.o, b * a.o_stride[0] + hq0 * a.o_stride[1]);
+          s.d_o = off(a.d_o, b * a.do_stride[0] + hq0 * a.do_stride[1]);
+          s.dq = const_cast<void*>(off(a.dq, b * a.dq_stride[0] + hq0 * a.dq_stride[1]));
+          s.k = off(a.k, b * a.k_stride[0] + hk0 * a.k_stride[1]);
+          s.v = off(a.v, b * a.v_stride[0] + hk0 * a.v_stride[1]);
+          s.dk = const_cast<void*>(off(a.dk, b * a.dk_stride[0] + hk0 * a.dk_stride[1]));
+          s.dv = const_cast<void*>(off(a.dv, b * a.dv_stride[0] + hk0 * a.dv_stride[1]));
+          s.lse = a.lse + ((int64_t)b * a.heads_q + hq0) * a.seqlen_q;
+          if (int rc = launch_bwd_sm100(s, stream)) return rc;
+        }
+      return FFPA_OK;
+    }
+  }
   const uint64_t need = align256(2ull * a.batch * a.heads_q * nq_pad * sizeof(float));  // lse2 + delta (split buffers optional)
   if (!a.workspace || a.workspace_bytes < need)
     return set_error(FFPA_ERR_INVALID_ARGUMENT, "backward workspace too small: need %llu bytes", (unsigned long long)need);
@@ -155,7 +198,7 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   kp.cu_k = a.cu_seqlens_k;
   kp.total_q = a.total_q; kp.total_k = a.total_k;
   // stash path: the dQ kernel writes P_drop / dS tiles, dK and dV become plain GEMMs over them
-  const uint64_t stash_one = varlen ? 0 : bwd_stash_bytes(B, Hq, Nq, Nkv, D);
+  const uint64_t stash_one = (varlen || plan.chunked) ? 0 : plan.one;
   const uint64_t stash_at = bwd_workspace_bytes_min(B, Hq, Hkv, Nq, Nkv, D);
   const bool use_stash = stash_one > 0 && a.workspace_bytes >= stash_at + 2 * stash_one;
   const int nk_pad = (Nkv + 255) / 256 * 256;

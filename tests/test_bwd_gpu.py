@@ -302,6 +302,30 @@ def test_backward_stash_path_matches_recompute_path_and_oracle(D, causal, shape)
   _cmp(sv, wv, tol, "dV")
 
 
+def test_backward_stash_chunked_by_memory_cap(monkeypatch):
+  """FFPA_BWD_STASH_MAX_GB bounds the score buffers: a larger problem runs as (batch element, KV-head range)
+  chunks through the same scratch. Results must equal the unchunked run bit for bit (same kernels, same
+  per-head arithmetic) and the workspace must respect the cap."""
+  from ffpa_attn import _C
+
+  B, Hq, Hkv, N, D = 2, 16, 8, 2048, 384
+  q, k, v, d_o = _mk(B, Hq, Hkv, N, N, D, torch.bfloat16, seed=23)
+  full_q, full_k, full_v, n_full = _raw_backward(q, k, v, d_o, True, False)
+  assert n_full == 4
+  ws_full = int(_C._lib.ffpa_b200_bwd_workspace_bytes(B, Hq, Hkv, N, N, D))
+  monkeypatch.setenv("FFPA_BWD_STASH_MAX_GB", "0.1")
+  ws_cap = int(_C._lib.ffpa_b200_bwd_workspace_bytes(B, Hq, Hkv, N, N, D))
+  assert ws_cap < 0.11 * 2 ** 30 + 2 ** 22 < ws_full
+  cq, ck, cv, n_chunked = _raw_backward(q, k, v, d_o, True, False)
+  assert n_chunked == 4 * 2 * 3   # 2 batch elements x KV-head chunks (3, 3, 2), 4 launches each
+  for a, b_ in ((cq, full_q), (ck, full_k), (cv, full_v)):
+    assert torch.equal(a, b_)
+  monkeypatch.setenv("FFPA_BWD_STASH_MAX_GB", "0.001")   # not even one KV head fits: recompute kernels
+  rq, rk, rv, _ = _raw_backward(q, k, v, d_o, True, False)
+  for a, b_ in ((rq, full_q), (rk, full_k), (rv, full_v)):
+    assert (a.float() - b_.float()).abs().max().item() < 2e-2 * max(1.0, b_.float().abs().max().item())
+
+
 def test_backward_stash_path_with_bias_and_dropout():
   """GENERAL variant of the stashing dQ kernel: P_drop (dropout applied) feeds dV, dS feeds dK."""
   import ffpa_attn
