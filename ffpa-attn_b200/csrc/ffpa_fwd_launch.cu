@@ -1,6 +1,7 @@
 // Host launcher of the forward: tensor-map construction (passed as __grid_constant__ kernel
 // parameters -- no per-launch cudaMalloc/cudaMemcpy as in
 // /root/reference/csrc/cuffpa/native/launch.cuh:503-509), persistent grid sizing, mode selection.
+#include <cstdlib>
 #include <vector>
 #include "ffpa_internal.h"
 #include "sm100_ptx.cuh"
@@ -9,11 +10,18 @@ namespace ffpa {
 
 template <bool BF16>
 int dispatch_fwd_dtype(int nqk, int mode, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                       const FwdKernelParams& kp, int nclusters, cudaStream_t stream);
+                       const CUtensorMap& msp, const FwdKernelParams& kp, int nclusters, cudaStream_t stream);
 extern template int dispatch_fwd_dtype<true>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                                             const FwdKernelParams&, int, cudaStream_t);
+                                             const CUtensorMap&, const FwdKernelParams&, int, cudaStream_t);
 extern template int dispatch_fwd_dtype<false>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                                              const FwdKernelParams&, int, cudaStream_t);
+                                              const CUtensorMap&, const FwdKernelParams&, int, cudaStream_t);
+namespace replay {
+template <bool BF16>
+int launch_fwd_replay(const CUtensorMap& map_p, const CUtensorMap& map_v, const FwdReplayParams& kp, int nclusters,
+                      cudaStream_t stream);
+extern template int launch_fwd_replay<true>(const CUtensorMap&, const CUtensorMap&, const FwdReplayParams&, int, cudaStream_t);
+extern template int launch_fwd_replay<false>(const CUtensorMap&, const CUtensorMap&, const FwdReplayParams&, int, cudaStream_t);
+}  // namespace replay
 
 template <bool BF16>
 int launch_merge_splits(const float* part_o, const float* part_lse, void* o, float* lse, const int64_t* ostride, int B,
@@ -38,7 +46,31 @@ int fwd_kv_splits(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_
   return s < 2 ? 1 : (int)s;
 }
 
+// Replay path for head dims > 768 (ffpa_fwd_replay_sm100.cuh): pass 0 stores its 16-bit P tiles, the per-tile O
+// rescale factors and 1 / rowsum so the second O slab is a GEMM instead of a second Q K^T + softmax pass.
+// FFPA_FWD_REPLAY=0 disables it, FFPA_FWD_REPLAY_MAX_GB (default 20) bounds the scratch (beyond: two passes).
+struct ReplayPlan { uint64_t p_bytes = 0, f_bytes = 0, inv_bytes = 0; int n_mt_even = 0, nk_pad = 0; uint64_t total() const { return p_bytes + f_bytes + inv_bytes; } };
+static ReplayPlan replay_plan(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
+  ReplayPlan pl;
+  const int nqk = (head_dim + 63) / 64, dvp = ((nqk * 64 + 127) / 128) * 128;
+  if (dvp <= 768) return pl;
+  const char* e = getenv("FFPA_FWD_REPLAY");
+  if (e && e[0] == '0') return pl;
+  const char* g = getenv("FFPA_FWD_REPLAY_MAX_GB");
+  const double cap = (g ? atof(g) : 20.0) * 1073741824.0;
+  const uint64_t bh = (uint64_t)batch * heads_q;
+  const int n_mt_even = (((seqlen_q + 127) / 128) + 1) & ~1, nk_pad = (seqlen_kv + 255) / 256 * 256;
+  const uint64_t p_bytes = bh * n_mt_even * 128ull * nk_pad * 2;
+  const uint64_t f_bytes = (bh * n_mt_even * (uint64_t)(nk_pad / 128) * 128 * 4 + 255) / 256 * 256;
+  const uint64_t inv_bytes = (bh * n_mt_even * 128 * 4 + 255) / 256 * 256;
+  if ((double)(p_bytes + f_bytes + inv_bytes) > cap) return pl;
+  pl.p_bytes = p_bytes; pl.f_bytes = f_bytes; pl.inv_bytes = inv_bytes; pl.n_mt_even = n_mt_even; pl.nk_pad = nk_pad;
+  return pl;
+}
+
 uint64_t fwd_split_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
+  const ReplayPlan rp = replay_plan(batch, heads_q, seqlen_q, seqlen_kv, head_dim);
+  if (rp.total() > 0) return rp.total() + 256;
   const int s = fwd_kv_splits(batch, heads_q, seqlen_q, seqlen_kv, head_dim);
   if (s <= 1) return 0;
   const uint64_t rows = (uint64_t)batch * heads_q * seqlen_q;
@@ -101,7 +133,27 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
       kp.part_lse = kp.part_o + (uint64_t)sp * rows * D;
     }
   }
-  kp.n_items = kp.n_mtiles * npass * kp.kv_splits * a.batch * a.heads_q;
+  // replay path (head dims > 768): one softmax pass that stores P / rescale factors / 1/rowsum, then a GEMM
+  const ReplayPlan rp = varlen ? ReplayPlan{} : replay_plan(a.batch, a.heads_q, a.seqlen_q, a.seqlen_kv, D);
+  const bool use_replay = rp.total() > 0 && a.workspace != nullptr && a.workspace_bytes >= rp.total() &&
+                          (reinterpret_cast<uintptr_t>(a.workspace) & 255u) == 0;
+  kp.stash_p = nullptr; kp.stash_f = nullptr; kp.stash_inv = nullptr;
+  kp.nk_pad = rp.nk_pad; kp.n_mt_even = rp.n_mt_even;
+  kp.n_pass = npass;
+  CUtensorMap msp = mq, mpl = mq;   // P store map ([64 x 64] boxes) / load map ([128 x 64] boxes) over the tile-major stash
+  if (use_replay) {
+    uint8_t* ws = static_cast<uint8_t*>(a.workspace);
+    kp.stash_p = ws;
+    kp.stash_f = reinterpret_cast<float*>(ws + rp.p_bytes);
+    kp.stash_inv = reinterpret_cast<float*>(ws + rp.p_bytes + rp.f_bytes);
+    kp.n_pass = 1;
+    const int sblocks = rp.n_mt_even * (rp.nk_pad / 64);
+    const int64_t sstr[4] = {(int64_t)sblocks * 8192, 8192, 64, 1};
+    if (!make_map(&msp, kp.stash_p, sstr, a.batch * a.heads_q, sblocks, 128, 64, 64, 64) ||
+        !make_map(&mpl, kp.stash_p, sstr, a.batch * a.heads_q, sblocks, 128, 64, 64, 128))
+      return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the forward replay stash");
+  }
+  kp.n_items = kp.n_mtiles * kp.n_pass * kp.kv_splits * a.batch * a.heads_q;
 
   int nclusters = sm_count() / 2;
   if (nclusters > kp.n_items) nclusters = kp.n_items;
@@ -114,7 +166,7 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
     const int off = a.seqlen_kv - a.seqlen_q, tc = (a.seqlen_kv + 127) / 128;
     for (int it = 0; it < kp.n_items; ++it) {
       const int mt = it % kp.n_mtiles;
-      int t = ((mt * 128 + 127 + off) >> 7) + 1;
+      int t = (((use_replay ? (mt * 128) | 128 : mt * 128) + 127 + off) >> 7) + 1;
       t = t < tc ? t : tc;
       cost[it] = (t < 1 ? 1 : t) * 16 + 24;  // tiles + fixed per-item overhead (prologue/epilogue ~1.5 tiles)
     }
@@ -123,9 +175,36 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   int mode = 0;  // fast
   if (a.dropout_p > 0.f) mode = 2;
   else if (a.bias_kind != FFPA_BIAS_NONE || !(a.softmax_scale > 0.f)) mode = 1;
-  int rc = (a.dtype == FFPA_DTYPE_BF16) ? dispatch_fwd_dtype<true>(nqk, mode, mq, mk, mv, kp, nclusters, stream)
-                                        : dispatch_fwd_dtype<false>(nqk, mode, mq, mk, mv, kp, nclusters, stream);
-  if (rc || kp.kv_splits == 1) return rc;
+  int rc = (a.dtype == FFPA_DTYPE_BF16) ? dispatch_fwd_dtype<true>(nqk, mode, mq, mk, mv, msp, kp, nclusters, stream)
+                                        : dispatch_fwd_dtype<false>(nqk, mode, mq, mk, mv, msp, kp, nclusters, stream);
+  if (rc) return rc;
+  if (use_replay) {
+    FwdReplayParams gp{};
+    gp.o = a.o;
+    for (int i = 0; i < 3; ++i) gp.o_stride[i] = a.o_stride[i];
+    gp.stash_f = kp.stash_f; gp.stash_inv = kp.stash_inv;
+    gp.batch = a.batch; gp.heads_q = a.heads_q; gp.heads_kv = a.heads_kv;
+    gp.seqlen_q = a.seqlen_q; gp.seqlen_kv = a.seqlen_kv; gp.head_dim = D; gp.causal = a.causal;
+    gp.nk_pad = rp.nk_pad; gp.n_mt_even = rp.n_mt_even;
+    gp.n_qblocks = rp.n_mt_even / 2;
+    gp.n_items = gp.n_qblocks * a.batch * a.heads_q;
+    int ncl = sm_count() / 2;
+    if (ncl > gp.n_items) ncl = gp.n_items;
+    gp.sched = nullptr; gp.sched_stride = 0;
+    if (a.causal && gp.n_items > ncl) {
+      std::vector<int> cost((size_t)gp.n_items);
+      const int off = a.seqlen_kv - a.seqlen_q, tc = (a.seqlen_kv + 127) / 128;
+      for (int it = 0; it < gp.n_items; ++it) {
+        int t = ((((it % gp.n_qblocks) * 256 + 128) + 127 + off) >> 7) + 1;
+        t = t < tc ? t : tc;
+        cost[it] = (t < 1 ? 1 : t) * 16 + 24;
+      }
+      gp.sched = get_schedule(cost.data(), gp.n_items, ncl, &gp.sched_stride, stream);
+    }
+    return (a.dtype == FFPA_DTYPE_BF16) ? replay::launch_fwd_replay<true>(mpl, mv, gp, ncl, stream)
+                                        : replay::launch_fwd_replay<false>(mpl, mv, gp, ncl, stream);
+  }
+  if (kp.kv_splits == 1) return rc;
   return (a.dtype == FFPA_DTYPE_BF16)
              ? launch_merge_splits<true>(kp.part_o, kp.part_lse, a.o, a.lse, a.o_stride, a.batch, a.heads_q, a.seqlen_q, D, kp.kv_splits, stream)
              : launch_merge_splits<false>(kp.part_o, kp.part_lse, a.o, a.lse, a.o_stride, a.batch, a.heads_q, a.seqlen_q, D, kp.kv_splits, stream);

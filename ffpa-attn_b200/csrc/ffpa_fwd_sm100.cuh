@@ -72,7 +72,9 @@ struct FwdCfg {
   static constexpr int CQ = ALT ? 1 : NSW / 4;   // column groups of the 64-column S stage
   static constexpr int CPT = 64 / CQ;            // S columns (keys) per thread and tile
   static constexpr int MMA_WARP = NSW, TMA_WARP = NSW + 1;
-  static constexpr int THREADS = (NSW + 2) * 32;
+  // two-slab head dims carry one more warp: it TMA-stores the P tiles for the replay path (see FwdKernelParams)
+  static constexpr int STORE_WARP = NSW + 2;
+  static constexpr int THREADS = (NSW + 2 + (DVP > 768 ? 1 : 0)) * 32;
   static constexpr int P_BYTES = KSTG * 16384;
   // Wide heads keep Q resident (96-128 KB), leaving too little for separate K and V rings; they use
   // ONE ring of 16 KB stages shared by K stages and V slices (a slice = 2 consecutive stages), so
@@ -101,6 +103,7 @@ struct Barriers {
   uint64_t s_full[4];
   uint64_t p_full[4], p_empty[4];
   uint64_t m_full[4];
+  uint64_t p_written[4], p_stored[4];   // replay path: P tile complete in this CTA / drained by the store warp
 };
 
 __device__ __forceinline__ int num_kv_tiles(int causal, int nq, int nkv, int q0) {
@@ -132,8 +135,8 @@ __device__ __forceinline__ FwdItem decode_fwd_item(const FwdKernelParams& p, uin
   FwdItem it;
   it.mt = item % p.n_mtiles;
   uint32_t rest = item / p.n_mtiles;
-  it.pass = rest % NPASS;
-  rest /= NPASS;
+  it.pass = rest % p.n_pass;
+  rest /= p.n_pass;
   it.split = rest % p.kv_splits;
   it.bh = rest / p.kv_splits;
   if (p.cu_q != nullptr) {
@@ -148,7 +151,9 @@ __device__ __forceinline__ FwdItem decode_fwd_item(const FwdKernelParams& p, uin
   } else {
     it.nq = p.seqlen_q; it.nkv = p.seqlen_kv; it.qoff = 0; it.koff = 0; it.bt = it.bh / p.heads_q;
   }
-  const int ttot = num_kv_tiles(p.causal, it.nq, it.nkv, it.mt * 128);
+  // replay path: the second-slab kernel consumes 256-row blocks, so both query tiles of a block visit the same
+  // KV tiles (the extra one of the even tile is fully masked and stores P = 0)
+  const int ttot = num_kv_tiles(p.causal, it.nq, it.nkv, p.stash_p != nullptr ? ((it.mt * 128) | 128) : it.mt * 128);
   if (p.kv_splits == 1) { it.tbeg = 0; it.T = ttot; }
   else {
     const int per = (ttot + p.kv_splits - 1) / p.kv_splits;
@@ -202,7 +207,8 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 template <int NQK, bool BF16, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FwdCfg<NQK>::THREADS, 1)
 ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                const __grid_constant__ CUtensorMap map_v, const FwdKernelParams p) {
+                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_sp,
+                const FwdKernelParams p) {
   using Cfg = FwdCfg<NQK>;
   constexpr int CG = 2;
   constexpr uint32_t KS = Cfg::KSTG;   // S/P pipeline depth
@@ -240,6 +246,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       ptx::mbar_init(bar(bars.p_full[i]), Cfg::ALT ? kSoftmaxWarps : 2 * kSoftmaxWarps);  // softmax warps (of one tile) of both CTAs
       ptx::mbar_init(bar(bars.m_full[i]), 2);
       ptx::mbar_init(bar(bars.p_empty[i]), 1);
+      ptx::mbar_init(bar(bars.p_written[i]), kSoftmaxWarps);
+      ptx::mbar_init(bar(bars.p_stored[i]), 1);
     }
     ptx::fence_mbar_init();
   }
@@ -431,6 +439,31 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
       }
+    }
+    __syncwarp();
+  } else if (Cfg::NPASS == 2 && warp == Cfg::STORE_WARP) {
+    // =========================================== P store warp (replay path) =====================
+    if (p.stash_p != nullptr && ptx::elect_one()) {
+      ptx::prefetch_tmap(&map_sp);
+      const uint64_t pol = ptx::l2_policy_evict_first();
+      uint32_t g = 0;
+      for (uint32_t kidx = 0;; ++kidx) {
+        const int item_s = next_item(p, cluster, nclusters, kidx);
+        if (item_s < 0) break;
+        const FwdItem fi = decode_fwd_item<Cfg::NPASS>(p, (uint32_t)item_s);
+        if (fi.T <= 0) continue;
+        for (int i = 0; i < fi.T; ++i, ++g) {
+          const uint32_t sbuf = g % KS;
+          const int blk = fi.mt * (p.nk_pad >> 6) + 2 * (fi.tbeg + i);
+          ptx::mbar_wait(bar(bars.p_written[sbuf]), (g / KS) & 1);
+          ptx::tma_store_4d_hint(&map_sp, sP + sbuf * 16384, 0, 64 * (int)rank, blk, fi.bh, pol);
+          ptx::tma_store_4d_hint(&map_sp, sP + sbuf * 16384 + 8192, 0, 64 * (int)rank, blk + 1, fi.bh, pol);
+          ptx::bulk_commit_group();
+          ptx::bulk_wait_group_read0();
+          ptx::mbar_arrive(bar(bars.p_stored[sbuf]));
+        }
+      }
+      ptx::bulk_wait_group0();
     }
     __syncwarp();
   } else {
@@ -625,6 +658,13 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
         // P buffer free? (PV of tile g-2 retired)
         ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((gi / KS) & 1) ^ 1);
+        const bool stash = Cfg::NPASS == 2 && p.stash_p != nullptr;
+        if (stash) {
+          ptx::mbar_wait(bar(bars.p_stored[sbuf]), ((gi / KS) & 1) ^ 1);   // ... and drained by the store warp
+          // O rescale factor of this (row, tile): what the second-slab GEMM replays (1 on most tiles)
+          if (kh == 0 && ch == 0)
+            p.stash_f[(((int64_t)bh * p.n_mt_even + mt) * (p.nk_pad >> 7) + ti) * 128 + 64 * (int)rank + (int)row] = factor;
+        }
         {
           const uint32_t prow = sP + sbuf * 16384 + kh * 8192 + row * 128;
 #pragma unroll
@@ -656,7 +696,10 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
-        if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(l_p_full0 + 8u * sbuf);  // p_full[] is contiguous
+        if (ptx::lane_id() == 0) {
+          ptx::mbar_arrive_cluster(l_p_full0 + 8u * sbuf);  // p_full[] is contiguous
+          if (stash) ptx::mbar_arrive(bar(bars.p_written[sbuf]));
+        }
         if constexpr (ALT) ++uw; else ++g;
       }
 
@@ -699,6 +742,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
         const bool row_ok = gq < seq_q;
+        if (Cfg::NPASS == 2 && p.stash_p != nullptr && wgi == 0 && kh == 0)
+          p.stash_inv[(int64_t)bh * p.n_mt_even * 128 + gq] = inv;
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
                         2 * ((int64_t)fi.bt * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)(fi.qoff + gq) * p.o_stride[2]);
 #pragma unroll
@@ -817,7 +862,7 @@ int launch_merge_splits(const float* part_o, const float* part_lse, void* o, flo
 // host launcher pieces (instantiated per dtype in ffpa_fwd_bf16.cu / ffpa_fwd_f16.cu)
 // ------------------------------------------------------------------------------------------------
 template <int NQK, bool BF16, int MODE>
-static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& msp,
                           const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
   using Cfg = FwdCfg<NQK>;
   auto kern = ffpa_fwd_kernel<NQK, BF16, MODE>;
@@ -831,7 +876,7 @@ static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CU
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
     attr_set[dev_id] = true;
   }
-  kern<<<dim3(2 * nclusters), dim3(Cfg::THREADS), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
+  kern<<<dim3(2 * nclusters), dim3(Cfg::THREADS), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, msp, kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "forward launch failed: %s", cudaGetErrorString(e));
   count_launch();
@@ -839,35 +884,35 @@ static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CU
 }
 
 template <bool BF16, int MODE>
-static int dispatch_nqk(int nqk, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+static int dispatch_nqk(int nqk, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& msp,
                         const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
   switch (nqk) {
-    case 1: return launch_variant<1, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 2: return launch_variant<2, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 3: return launch_variant<3, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 4: return launch_variant<4, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 5: return launch_variant<5, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 6: return launch_variant<6, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 7: return launch_variant<7, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 8: return launch_variant<8, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 9: return launch_variant<9, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 10: return launch_variant<10, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 11: return launch_variant<11, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 12: return launch_variant<12, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 13: return launch_variant<13, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 14: return launch_variant<14, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 15: return launch_variant<15, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
-    case 16: return launch_variant<16, BF16, MODE>(mq, mk, mv, kp, nclusters, stream);
+    case 1: return launch_variant<1, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 2: return launch_variant<2, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 3: return launch_variant<3, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 4: return launch_variant<4, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 5: return launch_variant<5, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 6: return launch_variant<6, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 7: return launch_variant<7, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 8: return launch_variant<8, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 9: return launch_variant<9, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 10: return launch_variant<10, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 11: return launch_variant<11, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 12: return launch_variant<12, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 13: return launch_variant<13, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 14: return launch_variant<14, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 15: return launch_variant<15, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 16: return launch_variant<16, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
     default: return set_error(FFPA_ERR_UNSUPPORTED, "head_dim > 1024 not supported");
   }
 }
 
 template <bool BF16>
-int dispatch_fwd_dtype(int nqk, int mode, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+int dispatch_fwd_dtype(int nqk, int mode, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& msp,
                        const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
-  if (mode == kModeFast) return dispatch_nqk<BF16, kModeFast>(nqk, mq, mk, mv, kp, nclusters, stream);
-  if (mode == kModeGeneral) return dispatch_nqk<BF16, kModeGeneral>(nqk, mq, mk, mv, kp, nclusters, stream);
-  return dispatch_nqk<BF16, kModeDropout>(nqk, mq, mk, mv, kp, nclusters, stream);
+  if (mode == kModeFast) return dispatch_nqk<BF16, kModeFast>(nqk, mq, mk, mv, msp, kp, nclusters, stream);
+  if (mode == kModeGeneral) return dispatch_nqk<BF16, kModeGeneral>(nqk, mq, mk, mv, msp, kp, nclusters, stream);
+  return dispatch_nqk<BF16, kModeDropout>(nqk, mq, mk, mv, msp, kp, nclusters, stream);
 }
 
 }  // namespace ffpa

@@ -31,6 +31,28 @@ struct FwdKernelParams {
   const int* cu_q;
   const int* cu_k;
   int total_q, total_k;
+  // Replay path for head dims > 768 (two O slabs): instead of recomputing S for the second slab, pass 0 stores
+  // its P tiles (16-bit, tile-major [B Hq][q tile][64-key block][128][64]), the O rescale factor of every
+  // (row, KV tile) and 1 / rowsum; ffpa_fwd_replay_kernel then computes O[:, 512:] = sum P V[:, 512:] as a
+  // GEMM that replays the rescales. n_pass = slab passes the items enumerate (1 when the replay path is on).
+  void* stash_p;
+  float* stash_f;    // [B Hq][q tiles (even)][KV tiles][128]
+  float* stash_inv;  // [B Hq][q tiles (even) * 128]
+  int nk_pad, n_mt_even, n_pass;
+};
+
+// second-slab forward GEMM over stashed P tiles (256 query rows per 2-CTA cluster, M = 256)
+struct FwdReplayParams {
+  void* o;
+  int64_t o_stride[3];
+  const float* stash_f;
+  const float* stash_inv;
+  int batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
+  int causal;
+  int nk_pad, n_mt_even;
+  int n_qblocks, n_items;   // 256-row blocks per (b, h)
+  const int* sched;
+  int sched_stride;
 };
 
 namespace bwd {

@@ -348,6 +348,53 @@ def test_large_headdims(D, causal):  # tests/test_ffpa_fwd.py:1226-1249 includes
   _check(out, ref, 2e-2, f"D={D}")
 
 
+@pytest.mark.parametrize("D", [776, 832, 896, 1024])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("shape", [(1, 2, 2, 384, 520), (2, 4, 2, 300, 300), (1, 2, 1, 1000, 1300), (1, 2, 2, 5, 257)])
+def test_replay_path_matches_two_pass_path_and_oracle(D, causal, shape, monkeypatch):
+  """Head dims > 768 (two O slabs): by default pass 0 stores its P tiles / rescale factors / 1/rowsum and
+  the second slab is a GEMM that replays them (csrc/ffpa_fwd_replay_sm100.cuh, 2 launches); with
+  FFPA_FWD_REPLAY=0 the second slab is a full second softmax pass (1 launch). Same P bits, same rescale
+  schedule -> the two paths must agree to rounding, and both with the oracle (GQA, tails, odd query-tile
+  counts, bottom-right causal)."""
+  import ffpa_attn
+
+  B, Hq, Hkv, Nq, Nkv = shape
+  q, k, v = _mk(B, Hq, Hkv, Nq, Nkv, D, torch.bfloat16, seed=31)
+  kw = dict(is_causal=causal, enable_gqa=Hq != Hkv)
+  n0 = ffpa_attn._C.launch_count()
+  o_replay, lse_replay = _lse(q, k, v, causal)
+  n_replay = ffpa_attn._C.launch_count() - n0
+  monkeypatch.setenv("FFPA_FWD_REPLAY", "0")
+  n0 = ffpa_attn._C.launch_count()
+  o_two, lse_two = _lse(q, k, v, causal)
+  n_two = ffpa_attn._C.launch_count() - n0
+  assert n_replay == 2 and n_two == 1
+  assert torch.equal(lse_replay, lse_two)
+  assert torch.equal(o_replay[..., :512], o_two[..., :512])   # first slab: the same kernel pass
+  assert (o_replay.float() - o_two.float()).abs().max().item() < 4e-3
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), causal=causal)
+  _check(o_replay, ref, 2e-2, f"replay D={D}")
+  del kw
+
+
+def test_replay_path_with_bias_dropout_fp16_and_large_amplitude():
+  """The replayed P is whatever pass 0 fed its MMA: bias and dropout included; large score amplitudes make
+  the row max move often, i.e. many rescale events to replay."""
+  import ffpa_attn
+
+  q, k, v = _mk(1, 2, 2, 300, 700, 1024, torch.float16, seed=32, amp=2.0)
+  bias = (torch.randn(1, 2, 300, 700, generator=torch.Generator().manual_seed(6)) * 3).to(DEV)
+  out = _run(q, k, v, attn_mask=bias)
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), bias=bias.cpu().double().numpy())
+  _check(out, ref, 1e-2, "bias, amp 2")
+  torch.cuda.manual_seed(77)
+  seed, offset = int(torch.cuda.initial_seed()), int(torch.cuda._get_rng_state_offset())
+  out = _run(q, k, v, dropout_p=0.2, is_causal=True)
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), causal=True, dropout_p=0.2, philox_seed=seed, philox_offset=offset)
+  _check(out, ref, 4e-2, "dropout causal")
+
+
 @pytest.mark.parametrize("H", [8, 16, 48])
 @pytest.mark.parametrize("D", [64, 192, 320, 576, 640])
 def test_dispatch_smoke_heads_by_headdim(H, D):  # tests/test_ffpa_fwd.py:44-45 (H x D dispatch grid)

@@ -64,6 +64,11 @@ def main():
     f = flops(B, Hq, Nq, Nkv, D, causal)
     ms_f = timeit(lambda: ffpa_attn.ffpa_attn_func(q, k, v, **kw), 10)
     rec = {"case": name, "fwd_ms": ms_f, "fwd_tflops": f / ms_f * 1e-9}
+    if D > 768:
+      os.environ["FFPA_FWD_REPLAY"] = "0"   # A/B: second O slab as a full second softmax pass
+      ms_2 = timeit(lambda: ffpa_attn.ffpa_attn_func(q, k, v, **kw), 10)
+      del os.environ["FFPA_FWD_REPLAY"]
+      rec.update({"fwd_two_pass_ms": ms_2, "fwd_two_pass_tflops": f / ms_2 * 1e-9})
     if name.startswith("decode"):
       kv_bytes = 2 * k.numel() * 2  # K and V are each read once: the HBM roofline of decode
       rec.update({"kv_gbs": kv_bytes / ms_f * 1e-6, "hbm_peak_gbs": 6580.9})
