@@ -204,6 +204,33 @@ def ffpa_attn_forward(Q, K, V, attn_bias, O, softmax_lse, stages, acc, causal, s
   if O.stride(3) != 1:
     raise RuntimeError("ffpa_attn_forward: O must have unit stride on the head dim")
 
+  # FP8 hybrid (reference: csrc/cuffpa/launch.cuh:341-374): the first n_early query rows run on the fp16/bf16
+  # kernel (they see few keys, so quantisation error weighs most there), rows [n_early, Nq) on the FP8 kernel.
+  # Bottom-right causal alignment makes both stages ordinary calls on zero-copy row views: stage 1 = the early
+  # rows against the keys they can see, stage 2 = the late rows against all keys.
+  if int(_lib.ffpa_b200_get_backend_impl()) == 5 and fp8_hybrid and int(causal) and Q.size(2) > int(fp8_hybrid_n_early) > 0:
+    n_early = int(fp8_hybrid_n_early)
+    if n_early % 128 != 0:
+      raise RuntimeError("ffpa_attn: fp8_hybrid_n_early must be multiple of 128")
+    nk_early = n_early + K.size(2) - Q.size(2)
+    want_lse = softmax_lse is not None and softmax_lse.numel() > 0
+    lse_e = torch.empty(Q.size(0), Q.size(1), n_early, dtype=torch.float32, device=Q.device) if want_lse else None
+    lse_l = torch.empty(Q.size(0), Q.size(1), Q.size(2) - n_early, dtype=torch.float32, device=Q.device) if want_lse else None
+    common = (stages, acc, causal, softmax_scale, dropout_p, philox_seed, philox_offset, fp8_smooth_k, fp8_smooth_v,
+              fp8_q_quant_method, fp8_k_quant_method, fp8_v_quant_method, fp8_pv_acc_type, fp8_qk_mm_type)
+    _lib.ffpa_b200_set_backend_impl(0)
+    try:
+      ffpa_attn_forward(Q[:, :, :n_early], K[:, :, :nk_early], V[:, :, :nk_early], attn_bias, O[:, :, :n_early], lse_e,
+                        *common, False, n_early, fp4_hybrid, fp4_hybrid_n_early)
+    finally:
+      _lib.ffpa_b200_set_backend_impl(5)
+    ffpa_attn_forward(Q[:, :, n_early:], K, V, attn_bias, O[:, :, n_early:], lse_l, *common, False, n_early,
+                      fp4_hybrid, fp4_hybrid_n_early)
+    if want_lse:
+      softmax_lse[:, :, :n_early].copy_(lse_e)
+      softmax_lse[:, :, n_early:].copy_(lse_l)
+    return
+
   p = _FwdParams()
   p.q, p.k, p.v, p.o = Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr()
   if softmax_lse is not None and softmax_lse.numel() > 0:

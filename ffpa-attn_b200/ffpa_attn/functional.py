@@ -193,6 +193,12 @@ class FFPAAttnMeta:
     self.attn_meta.dropout_p = float(dropout_p)
     self.attn_meta.is_grad_enabled = torch.is_grad_enabled()
     self.forward_meta.is_causal = bool(is_causal)
+    # *_hybrid=None means "auto": on when causal + the matching quant path, to protect the precision of the early
+    # rows (reference: functional.py:781-794); explicit True / False is honoured as given
+    if self.forward_meta.fp8_hybrid is None:
+      self.forward_meta.fp8_hybrid = bool(self.forward_meta.enable_fp8 and is_causal)
+    if self.forward_meta.fp4_hybrid is None:
+      self.forward_meta.fp4_hybrid = False
     if query.dtype not in (torch.float16, torch.bfloat16):
       raise TypeError(f"ffpa_attn_func only supports fp16/bf16, got {query.dtype}")
     if key.dtype != query.dtype or value.dtype != query.dtype:

@@ -28,8 +28,10 @@ def _fp8(q, k, v, smooth_k=True, **kw):
   be = ffpa_attn.CUDABackend(enable_fp8=True, fp8_smooth_k=smooth_k)
   out = ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=be, **kw)
   torch.cuda.synchronize()
-  # quantise + attention (+ K column sums + q.mean for smooth-K)
-  assert ffpa_attn._C.launch_count() - n0 == (4 if smooth_k else 2)
+  # quantise + attention (+ K column sums + q.mean for smooth-K); causal calls with more than 256 query rows run
+  # the hybrid (reference default, functional.py:781-794): one bf16/fp16 launch for the early rows on top
+  hybrid = 1 if (kw.get("is_causal") and q.size(2) > 256) else 0
+  assert ffpa_attn._C.launch_count() - n0 == (4 if smooth_k else 2) + hybrid
   return out
 
 
@@ -50,6 +52,38 @@ def test_fp8_causal_and_tails(Nq, Nkv):
   out = _fp8(q, k, v, is_causal=True, enable_gqa=True)
   ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), causal=True)
   assert np.abs(out.float().cpu().numpy() - ref).max() < 1e-1
+
+
+def test_fp8_hybrid_early_rows_in_16_bit():
+  """fp8_hybrid (reference: launch.cuh:341-374; auto-on for causal FP8): rows [0, n_early) come from the
+  fp16/bf16 kernel -- they must match the 16-bit kernel's output -- and rows [n_early, Nq) from the FP8 kernel
+  -- they must match the non-hybrid FP8 output; LSE is stitched the same way."""
+  import ffpa_attn
+  from ffpa_attn.cuda import _ffpa_attn_forward_cuda
+  import ffpa_attn.cuda as fc
+
+  q, k, v = _mk(1, 4, 2, 700, 900, 256, torch.bfloat16, seed=5)
+  scale = 256 ** -0.5
+  ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.AUTO)   # the hint is process-global: earlier tests left it at FP8
+  o16, lse16 = _ffpa_attn_forward_cuda(q, k, v, None, None, 0, 1, 1, scale)
+  ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.CUTE_TMA_FP8)
+  try:
+    o8, lse8 = _ffpa_attn_forward_cuda(q, k, v, None, None, 0, 1, 1, scale, fp8_hybrid=False)
+    oh, lseh = _ffpa_attn_forward_cuda(q, k, v, None, None, 0, 1, 1, scale, fp8_hybrid=True, fp8_hybrid_n_early=256)
+    with pytest.raises(RuntimeError):
+      _ffpa_attn_forward_cuda(q, k, v, None, None, 0, 1, 1, scale, fp8_hybrid=True, fp8_hybrid_n_early=200)
+  finally:
+    ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.AUTO)
+  torch.cuda.synchronize()
+  assert (oh[:, :, :256].float() - o16[:, :, :256].float()).abs().max().item() < 2e-3
+  assert (lseh[:, :, :256] - lse16[:, :, :256]).abs().max().item() < 1e-4
+  # late rows: the same FP8 kernel on a row view (quantisation-noise level agreement with the full FP8 call)
+  assert (oh[:, :, 256:].float() - o8[:, :, 256:].float()).abs().max().item() < 2e-2
+  assert (lseh[:, :, 256:] - lse8[:, :, 256:]).abs().max().item() < 5e-2
+  ref, lref = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), causal=True)
+  e_h = np.abs(oh.float().cpu().numpy() - ref)
+  e_8 = np.abs(o8.float().cpu().numpy() - ref)
+  assert e_h.max() < 1e-1 and e_h[:, :, :256].max() <= e_8[:, :, :256].max() + 1e-3
 
 
 def test_fp8_lse_and_large_amplitude():
