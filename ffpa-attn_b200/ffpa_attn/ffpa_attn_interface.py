@@ -101,6 +101,9 @@ def ffpa_attn_varlen_func(
     raise ValueError("H_q must be an integer multiple of H_kv")
   if q.size(2) % 8 != 0 or q.size(2) > 1024:
     raise NotImplementedError(f"ffpa_attn_varlen_func supports head_dim % 8 == 0 and <= 1024, got {q.size(2)}")
+  for t in (q, k, v, cu_seqlens_q, cu_seqlens_k):
+    if t.device.type != "cuda":
+      raise RuntimeError("ffpa_attn_varlen_func: all tensors must be CUDA tensors (there is no CPU / SDPA fallback path)")
   if q.size(0) == 0 or k.size(0) == 0:
     out = torch.zeros_like(q)
     lse = torch.full((q.size(1), q.size(0)), float("-inf"), dtype=torch.float32, device=q.device)

@@ -234,3 +234,89 @@ def test_fake_op_registered_for_compile():
   o, lse = torch.ops.ffpa_attn._fwd_cuda(q, q, q, q.new_empty(0), 0, 1, 0, 0.125, 0.0, 0, 0, True, False,
                                          0, 0, 0, 0, 0, False, 256, False, 256)
   assert o.shape == q.shape and lse.shape == (1, 2, 16) and lse.dtype == torch.float32
+
+
+# ---- packed variable-length entry, workspace plans, hybrid resolution (host logic only) ----
+def test_varlen_host_validation_and_no_cpu_fallback():
+  """Reference checks (cute/__init__.py:466-571): dtypes and shapes only, cu_seqlens values are never read on
+  the host; CPU tensors must fail loudly."""
+  from ffpa_attn import ffpa_attn_varlen_func
+
+  q = torch.randn(32, 2, 64, dtype=torch.bfloat16)
+  k = torch.randn(32, 2, 64, dtype=torch.bfloat16)
+  cu = torch.tensor([0, 16, 32], dtype=torch.int32)
+  with pytest.raises(TypeError, match="int32"):
+    ffpa_attn_varlen_func(q, k, k, cu.long(), cu, 16, 16)
+  with pytest.raises(NotImplementedError):
+    ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16, dropout_p=0.1)
+  with pytest.raises(NotImplementedError, match="softcap"):
+    ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16, softcap=1.0)
+  with pytest.raises(TypeError, match="unexpected"):
+    ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16, bogus=1)
+  with pytest.raises(ValueError, match="enable_gqa"):
+    ffpa_attn_varlen_func(q, k[:, :1], k[:, :1], cu, cu, 16, 16)
+  with pytest.raises(ValueError, match="same batch"):
+    ffpa_attn_varlen_func(q, k, k, cu, cu[:-1], 16, 16)
+  with pytest.raises(ValueError, match="THD"):
+    ffpa_attn_varlen_func(q[None], k[None], k[None], cu, cu, 16, 16)
+  with pytest.raises(TypeError, match="fp16/bf16"):
+    ffpa_attn_varlen_func(q.float(), k.float(), k.float(), cu, cu, 16, 16)
+  with pytest.raises(ValueError, match="only backend"):
+    ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16, backend="cutedsl")
+  with pytest.raises(RuntimeError, match="no CPU"):
+    ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16)
+
+
+def test_backward_workspace_plan(lib, monkeypatch):
+  """ffpa_b200_bwd_workspace_bytes = required scratch + the two 16-bit score buffers of the stash path for head
+  dims 384..1024, bounded by FFPA_BWD_STASH_MAX_GB (KV-head chunks beyond it); _min = required scratch only."""
+  f, m = lib.ffpa_b200_bwd_workspace_bytes, lib.ffpa_b200_bwd_workspace_bytes_min
+  for fn in (f, m):
+    fn.argtypes = [ctypes.c_int32] * 6
+    fn.restype = ctypes.c_uint64
+  monkeypatch.delenv("FFPA_BWD_STASH_MAX_GB", raising=False)
+  monkeypatch.delenv("FFPA_BWD_STASH", raising=False)
+  B, H, N, D = 1, 32, 8192, 512
+  stash = 2 * B * H * N * N * 2
+  assert f(B, H, H, N, N, D) == m(B, H, H, N, N, D) + stash
+  assert f(B, H, H, N, N, 256) == m(B, H, H, N, N, 256)            # small heads: recompute kernels
+  assert f(B, H, H, N, N, 1024) == m(B, H, H, N, N, 1024) + stash   # large heads: stash on the first slab pass
+  assert f(1, 4, 2, 130, 257, 512) == m(1, 4, 2, 130, 257, 512) + 2 * 4 * 256 * 512 * 2   # padded to 128 x 256
+  # 4 batch elements would need 34 GB: chunked per batch element under the default 20 GB cap
+  assert f(4, H, H, N, N, D) <= 20 * 2 ** 30 + m(4, H, H, N, N, D)
+  assert f(4, H, H, N, N, D) >= stash
+  monkeypatch.setenv("FFPA_BWD_STASH", "0")
+  assert f(B, H, H, N, N, D) == m(B, H, H, N, N, D)
+
+
+def test_forward_workspace_plan(lib, monkeypatch):
+  """Forward scratch: KV-split partials for decode-like shapes, the replay stash for head dims > 768, FP8 copies."""
+  f = lib.ffpa_b200_fwd_workspace_bytes
+  f.argtypes = [ctypes.c_int32] * 7
+  f.restype = ctypes.c_uint64
+  monkeypatch.delenv("FFPA_FWD_REPLAY", raising=False)
+  monkeypatch.delenv("FFPA_FWD_REPLAY_MAX_GB", raising=False)
+  assert f(1, 32, 32, 8192, 8192, 512, 0) == 0
+  assert f(1, 32, 32, 8192, 8192, 768, 0) == 0
+  need = f(1, 32, 32, 8192, 8192, 1024, 0)
+  assert 32 * 8192 * 8192 * 2 <= need <= 32 * 8192 * 8192 * 2 * 1.02   # P tiles + factors + 1/rowsum
+  assert f(1, 32, 32, 1, 8192, 512, 0) > 0     # decode: KV-split partials
+  assert f(1, 32, 32, 8192, 8192, 256, 1) > 3 * 32 * 8192 * 256   # FP8: e4m3 copies of Q, K, V + scales
+  monkeypatch.setenv("FFPA_FWD_REPLAY", "0")
+  assert f(1, 32, 32, 8192, 8192, 1024, 0) == 0
+
+
+def test_fp8_hybrid_auto_resolution():
+  """*_hybrid=None resolves to (enable_fp8 and is_causal) in normalize_inputs (reference functional.py:781-794)."""
+  from ffpa_attn import CUDABackend, FFPAAttnMeta
+
+  q, k, v = _qkv()
+  for causal, fp8, want in ((True, True, True), (False, True, False), (True, False, False)):
+    meta = FFPAAttnMeta.from_kwargs(forward_backend=CUDABackend(enable_fp8=fp8))
+    with pytest.raises(RuntimeError, match="no CPU"):   # CPU tensors are rejected after the switches are resolved
+      meta.normalize_inputs(q, k, v, None, 0.0, causal, None, False)
+    assert meta.forward_meta.fp8_hybrid is want
+  meta = FFPAAttnMeta.from_kwargs(forward_backend=CUDABackend(enable_fp8=True, fp8_hybrid=False))
+  with pytest.raises(RuntimeError, match="no CPU"):
+    meta.normalize_inputs(q, k, v, None, 0.0, True, None, False)
+  assert meta.forward_meta.fp8_hybrid is False
