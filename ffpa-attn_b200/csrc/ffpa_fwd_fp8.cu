@@ -8,7 +8,7 @@ static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a
 
 struct Fp8Layout {
   int dpad, tq, tk;
-  uint64_t off_q8, off_k8, off_v8, off_qs, off_ks, off_vs, off_vref, off_ksum, off_qkm, total;
+  uint64_t off_q8, off_k8, off_v8, off_qs, off_ks, off_vs, off_vref, off_ksum, off_vsum, off_qkm, total;
 };
 
 static Fp8Layout fp8_layout(int B, int Hq, int Hkv, int Nq, int Nkv, int D) {
@@ -25,6 +25,7 @@ static Fp8Layout fp8_layout(int B, int Hq, int Hkv, int Nq, int Nkv, int D) {
   L.off_vs = o; o = align_up(o + (uint64_t)B * Hkv * L.tk * 4, 256);
   L.off_vref = o; o = align_up(o + (uint64_t)B * Hkv * 4, 256);
   L.off_ksum = o; o = align_up(o + (uint64_t)B * Hkv * D * 4, 256);
+  L.off_vsum = o; o = align_up(o + (uint64_t)B * Hkv * D * 4, 256);
   L.off_qkm = o; o = align_up(o + (uint64_t)B * Hq * Nq * 4, 256);
   L.total = o;
   return L;
@@ -111,6 +112,24 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
     count_launch();
     qa.ksum = ksum;
   }
+  // smooth-V (a.fp8 bit 2; reference knob fp8_smooth_v): quantise V - mean_seq(V), add the mean back to O
+  const bool smooth_v = (a.fp8 & 4) != 0;
+  float* vsum = reinterpret_cast<float*>(ws + L.off_vsum);
+  qa.vsum = nullptr;
+  if (smooth_v) {
+    e = cudaMemsetAsync(vsum, 0, (size_t)B * Hkv * D * 4, stream);
+    if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    const int rpb = 256;
+    const unsigned nblk = (unsigned)((Nkv + rpb - 1) / rpb) * Hkv * B;
+    if (a.dtype == FFPA_DTYPE_BF16)
+      fp8::k_colsum_kernel<true><<<nblk, 256, 0, stream>>>(a.v, vsum, a.v_stride[0], a.v_stride[1], a.v_stride[2], Hkv, Nkv, D, rpb);
+    else
+      fp8::k_colsum_kernel<false><<<nblk, 256, 0, stream>>>(a.v, vsum, a.v_stride[0], a.v_stride[1], a.v_stride[2], Hkv, Nkv, D, rpb);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "smooth-V pre-pass launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    qa.vsum = vsum;
+  }
   if (a.dtype == FFPA_DTYPE_BF16)
     fp8::quantize_e4m3_kernel<true><<<dim3((unsigned)qa.first_block[3]), dim3(fp8::kQuantThreads), 0, stream>>>(qa);
   else
@@ -129,6 +148,7 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   for (int i = 0; i < 3; ++i) kp.o_stride[i] = a.o_stride[i];
   kp.qs = qa.scale[0]; kp.ks = qa.scale[1]; kp.vs = qa.scale[2]; kp.vref = qa.vref;
   kp.qkm = smooth_k ? qkm : nullptr;
+  kp.vsum = smooth_v ? vsum : nullptr;
   kp.tq = L.tq; kp.tk = L.tk;
   kp.batch = B; kp.heads_q = Hq; kp.heads_kv = Hkv; kp.seqlen_q = Nq; kp.seqlen_kv = Nkv; kp.head_dim = D;
   kp.causal = a.causal;

@@ -40,6 +40,7 @@ struct Fp8KernelParams {
   const float* vs;     // [B, Hkv, TK]
   const float* vref;   // [B, Hkv]
   const float* qkm;    // [B, Hq, Nq]  q . mean_seq(K) (smooth-K LSE correction) or nullptr
+  const float* vsum;   // [B, Hkv, D]  column sums of V over the sequence (smooth-V: added back as mean) or nullptr
   int tq, tk;
   int batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
   int causal;
@@ -445,6 +446,10 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         ptx::tc_fence_after();
         const float inv = l_tot > 0.f ? (vref / kPScale) / l_tot : 0.f;
         const bool row_ok = gq < p.seqlen_q;
+        // smooth-V: the kernel saw V - mean_seq(V); rows of P sum to 1, so O = P (V - mean) + mean
+        // (reference knob fp8_smooth_v, functional.py:247). Rows without a visible key stay 0.
+        const float* vmean = (p.vsum != nullptr && l_tot > 0.f) ? p.vsum + ((int64_t)b * p.heads_kv + h / (p.heads_q / p.heads_kv)) * p.head_dim : nullptr;
+        const float inv_nkv = 1.f / (float)p.seqlen_kv;
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
                         2 * ((int64_t)b * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)gq * p.o_stride[2]);
 #pragma unroll
@@ -463,8 +468,9 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                   uint32_t w[4];
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
-                    const float a = __uint_as_float(orr[8 * v + 2 * u]) * inv;
-                    const float c = __uint_as_float(orr[8 * v + 2 * u + 1]) * inv;
+                    float a = __uint_as_float(orr[8 * v + 2 * u]) * inv;
+                    float c = __uint_as_float(orr[8 * v + 2 * u + 1]) * inv;
+                    if (vmean != nullptr) { a = fmaf(__ldg(vmean + d + 2 * u), inv_nkv, a); c = fmaf(__ldg(vmean + d + 2 * u + 1), inv_nkv, c); }
                     w[u] = OUT_BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
                   }
                   *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -509,6 +515,7 @@ struct QuantArgs {
   int64_t first_block[4];  // prefix sums of blocks per tensor
   int batch, head_dim, dpad;
   const float* ksum;       // [B, Hkv, D] column sums of K over the sequence (smooth-K) or nullptr
+  const float* vsum;       // [B, Hkv, D] column sums of V over the sequence (smooth-V) or nullptr
 };
 
 // One 1024-thread block per (tensor, b, h, 128-row block): the tile (<= 128 x 512 x 2 B) is read from HBM
@@ -533,7 +540,8 @@ __global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const Q
   const int vec_per_row = D / 8;               // 8 elements (16 B) per vector; D % 8 == 0
   const int nvec = rows * vec_per_row;         // <= 128 * 64 = 8 * 1024
   // smooth-K: quantise K - mean_seq(K) (per (b, h) and channel)
-  const float* km = (which == 1 && a.ksum != nullptr) ? a.ksum + ((int64_t)b * H + h) * D : nullptr;
+  const float* km = (which == 1 && a.ksum != nullptr) ? a.ksum + ((int64_t)b * H + h) * D
+                  : (which == 2 && a.vsum != nullptr) ? a.vsum + ((int64_t)b * H + h) * D : nullptr;
   const float inv_n = 1.f / (float)N;
   constexpr int MAXV = 8;
   uint4 cache[MAXV];

@@ -86,6 +86,26 @@ def test_fp8_hybrid_early_rows_in_16_bit():
   assert e_h.max() < 1e-1 and e_h[:, :, :256].max() <= e_8[:, :, :256].max() + 1e-3
 
 
+def test_fp8_smooth_v_removes_channel_mean_error():
+  """fp8_smooth_v (reference knob, functional.py:247): V - mean_seq(V) is quantised and the mean is added back to
+  O (rows of P sum to 1). With a large per-channel offset in V the e4m3 range is no longer spent on the offset."""
+  import ffpa_attn
+
+  q, k, v = _mk(1, 4, 2, 600, 900, 256, torch.bfloat16, seed=6)
+  v = (v.float() + 3.0 * torch.randn(1, 2, 1, 256, generator=torch.Generator().manual_seed(1)).to(DEV)).to(torch.bfloat16)
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), causal=True)
+  errs = {}
+  for sv in (False, True):
+    n0 = ffpa_attn._C.launch_count()
+    be = ffpa_attn.CUDABackend(enable_fp8=True, fp8_smooth_v=sv, fp8_hybrid=False)
+    out = ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=be, is_causal=True, enable_gqa=True)
+    torch.cuda.synchronize()
+    assert ffpa_attn._C.launch_count() - n0 == 4 + (1 if sv else 0)
+    errs[sv] = float(np.abs(out.float().cpu().numpy() - ref).max())
+  assert errs[True] < 4e-2, errs
+  assert errs[True] < 0.5 * errs[False], errs
+
+
 def test_fp8_lse_and_large_amplitude():
   import ffpa_attn
   import ffpa_attn.cuda as fc
