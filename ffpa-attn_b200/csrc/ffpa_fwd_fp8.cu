@@ -8,7 +8,7 @@ static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a
 
 struct Fp8Layout {
   int dpad, tq, tk;
-  uint64_t off_q8, off_k8, off_v8, off_qs, off_ks, off_vs, off_vref, off_ksum, off_vsum, off_qkm, total;
+  uint64_t off_q8, off_k8, off_v8, off_qs, off_ks, off_vs, off_vref, off_ksum, off_vsum, off_vamax, off_qkm, total;
 };
 
 static Fp8Layout fp8_layout(int B, int Hq, int Hkv, int Nq, int Nkv, int D) {
@@ -26,6 +26,7 @@ static Fp8Layout fp8_layout(int B, int Hq, int Hkv, int Nq, int Nkv, int D) {
   L.off_vref = o; o = align_up(o + (uint64_t)B * Hkv * 4, 256);
   L.off_ksum = o; o = align_up(o + (uint64_t)B * Hkv * D * 4, 256);
   L.off_vsum = o; o = align_up(o + (uint64_t)B * Hkv * D * 4, 256);
+  L.off_vamax = o; o = align_up(o + (uint64_t)B * Hkv * D * 4, 256);
   L.off_qkm = o; o = align_up(o + (uint64_t)B * Hq * Nq * 4, 256);
   L.total = o;
   return L;
@@ -130,6 +131,24 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
     count_launch();
     qa.vsum = vsum;
   }
+  // per-channel V scales (a.fp8 bit 3; reference knob fp8_v_quant_method="per_channel")
+  const bool v_per_channel = (a.fp8 & 8) != 0;
+  float* vamax = reinterpret_cast<float*>(ws + L.off_vamax);
+  qa.vamax = nullptr;
+  if (v_per_channel) {
+    e = cudaMemsetAsync(vamax, 0, (size_t)B * Hkv * D * 4, stream);
+    if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    const int rpb = 256;
+    const unsigned nblk = (unsigned)((Nkv + rpb - 1) / rpb) * Hkv * B;
+    if (a.dtype == FFPA_DTYPE_BF16)
+      fp8::v_colamax_kernel<true><<<nblk, 256, 0, stream>>>(a.v, qa.vsum, vamax, a.v_stride[0], a.v_stride[1], a.v_stride[2], Hkv, Nkv, D, rpb);
+    else
+      fp8::v_colamax_kernel<false><<<nblk, 256, 0, stream>>>(a.v, qa.vsum, vamax, a.v_stride[0], a.v_stride[1], a.v_stride[2], Hkv, Nkv, D, rpb);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "per-channel V pre-pass launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    qa.vamax = vamax;
+  }
   if (a.dtype == FFPA_DTYPE_BF16)
     fp8::quantize_e4m3_kernel<true><<<dim3((unsigned)qa.first_block[3]), dim3(fp8::kQuantThreads), 0, stream>>>(qa);
   else
@@ -149,6 +168,7 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   kp.qs = qa.scale[0]; kp.ks = qa.scale[1]; kp.vs = qa.scale[2]; kp.vref = qa.vref;
   kp.qkm = smooth_k ? qkm : nullptr;
   kp.vsum = smooth_v ? vsum : nullptr;
+  kp.vamax = v_per_channel ? vamax : nullptr;
   kp.tq = L.tq; kp.tk = L.tk;
   kp.batch = B; kp.heads_q = Hq; kp.heads_kv = Hkv; kp.seqlen_q = Nq; kp.seqlen_kv = Nkv; kp.head_dim = D;
   kp.causal = a.causal;

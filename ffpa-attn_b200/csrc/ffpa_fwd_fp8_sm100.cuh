@@ -41,6 +41,7 @@ struct Fp8KernelParams {
   const float* vref;   // [B, Hkv]
   const float* qkm;    // [B, Hq, Nq]  q . mean_seq(K) (smooth-K LSE correction) or nullptr
   const float* vsum;   // [B, Hkv, D]  column sums of V over the sequence (smooth-V: added back as mean) or nullptr
+  const float* vamax;  // [B, Hkv, D]  per-channel |V| maxima (per-channel V scales, applied in the epilogue) or nullptr
   int tq, tk;
   int batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim;
   int causal;
@@ -450,6 +451,9 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         // (reference knob fp8_smooth_v, functional.py:247). Rows without a visible key stay 0.
         const float* vmean = (p.vsum != nullptr && l_tot > 0.f) ? p.vsum + ((int64_t)b * p.heads_kv + h / (p.heads_q / p.heads_kv)) * p.head_dim : nullptr;
         const float inv_nkv = 1.f / (float)p.seqlen_kv;
+        // per-channel V scales (reference knob fp8_v_quant_method="per_channel"): V8[k, d] = V[k, d] / cs[d], block scales
+        // are 1, so O[d] is scaled by cs[d] = amax[d] / 448 here
+        const float* vcs = p.vamax != nullptr ? p.vamax + ((int64_t)b * p.heads_kv + h / (p.heads_q / p.heads_kv)) * p.head_dim : nullptr;
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
                         2 * ((int64_t)b * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)gq * p.o_stride[2]);
 #pragma unroll
@@ -470,6 +474,10 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                   for (int u = 0; u < 4; ++u) {
                     float a = __uint_as_float(orr[8 * v + 2 * u]) * inv;
                     float c = __uint_as_float(orr[8 * v + 2 * u + 1]) * inv;
+                    if (vcs != nullptr) {
+                      a *= fmaxf(__ldg(vcs + d + 2 * u), 1e-12f) * (1.f / 448.f);
+                      c *= fmaxf(__ldg(vcs + d + 2 * u + 1), 1e-12f) * (1.f / 448.f);
+                    }
                     if (vmean != nullptr) { a = fmaf(__ldg(vmean + d + 2 * u), inv_nkv, a); c = fmaf(__ldg(vmean + d + 2 * u + 1), inv_nkv, c); }
                     w[u] = OUT_BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
                   }
@@ -516,6 +524,7 @@ struct QuantArgs {
   int batch, head_dim, dpad;
   const float* ksum;       // [B, Hkv, D] column sums of K over the sequence (smooth-K) or nullptr
   const float* vsum;       // [B, Hkv, D] column sums of V over the sequence (smooth-V) or nullptr
+  const float* vamax;      // [B, Hkv, D] per-channel maxima of |V - mean| (per-channel V quantisation) or nullptr
 };
 
 // One 1024-thread block per (tensor, b, h, 128-row block): the tile (<= 128 x 512 x 2 B) is read from HBM
@@ -578,7 +587,9 @@ __global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const Q
   amax = red[0];
 #pragma unroll
   for (int i = 1; i < 32; ++i) amax = fmaxf(amax, red[i]);
-  const float scale = fmaxf(amax, 1e-12f) / 448.f;
+  // per-channel V: every channel has its own scale (applied in the attention epilogue), block scale = 1
+  const float* cam = (which == 2 && a.vamax != nullptr) ? a.vamax + ((int64_t)b * H + h) * D : nullptr;
+  const float scale = cam != nullptr ? 1.f : fmaxf(amax, 1e-12f) / 448.f;
   const float inv = 1.f / scale;
   if (threadIdx.x == 0) {
     a.scale[which][((int64_t)b * H + h) * T + tile] = scale;
@@ -592,6 +603,10 @@ __global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const Q
       const int r = i / vec_per_row, c = i % vec_per_row;
       float f[8];
       expand(cache[v], c, f);
+      if (cam != nullptr) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] *= 448.f / fmaxf(__ldg(cam + 8 * c + u), 1e-12f);
+      }
       uint2 o;
       o.x = pack_e4m3x4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
       o.y = pack_e4m3x4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
@@ -649,6 +664,54 @@ __global__ void __launch_bounds__(256) k_colsum_kernel(const void* __restrict__ 
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
       atomicAdd(ksum + ((int64_t)b * H + h) * D + dd, t);
+    }
+    __syncthreads();
+  }
+}
+
+// per-channel maxima of |V - mean| over the sequence (same decomposition as k_colsum_kernel; non-negative floats
+// order like their bit patterns, so chunks combine with an integer atomicMax)
+template <bool BF16>
+__global__ void __launch_bounds__(256) v_colamax_kernel(const void* __restrict__ v, const float* __restrict__ vsum,
+                                                        float* __restrict__ vamax, int64_t s0, int64_t s1, int64_t s2, int H,
+                                                        int N, int D, int rows_per_block) {
+  __shared__ float part[8][256];
+  const int nchunk = (N + rows_per_block - 1) / rows_per_block;
+  const int chunk = blockIdx.x % nchunk;
+  const int h = (blockIdx.x / nchunk) % H;
+  const int b = blockIdx.x / (nchunk * H);
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(v) + 2 * ((int64_t)b * s0 + (int64_t)h * s1);
+  const float* mean = vsum != nullptr ? vsum + ((int64_t)b * H + h) * D : nullptr;
+  const float inv_n = 1.f / (float)N;
+  const int r0 = chunk * rows_per_block;
+  const int r1 = (r0 + rows_per_block) < N ? (r0 + rows_per_block) : N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int d0 = 0; d0 < D; d0 += 256) {
+    const int d = d0 + 8 * lane;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (d < D) {
+      float mu[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (mean != nullptr) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mu[u] = mean[d + u] * inv_n;
+      }
+#pragma unroll 4
+      for (int r = r0 + warp; r < r1; r += 8) {
+        float f[8];
+        unpack8<BF16>(*reinterpret_cast<const uint4*>(src + 2 * ((int64_t)r * s2 + d)), f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = fmaxf(acc[u], fabsf(f[u] - mu[u]));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) part[warp][8 * lane + u] = acc[u];
+    __syncthreads();
+    const int dd = d0 + threadIdx.x;
+    if (dd < D) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t = fmaxf(t, part[w][threadIdx.x]);
+      atomicMax(reinterpret_cast<unsigned int*>(vamax + ((int64_t)b * H + h) * D + dd), __float_as_uint(t));
     }
     __syncthreads();
   }

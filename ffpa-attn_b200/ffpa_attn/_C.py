@@ -247,7 +247,9 @@ def ffpa_attn_forward(Q, K, V, attn_bias, O, softmax_lse, stages, acc, causal, s
   p.dtype = dt
   p.causal = int(causal)
   # bit 0: FP8 path (backend hint CUTE_TMA_FP8); bit 1: smooth-K (fp8_smooth_k, default True as in the reference)
-  p.fp8 = (1 | (2 if fp8_smooth_k else 0) | (4 if fp8_smooth_v else 0)) if int(_lib.ffpa_b200_get_backend_impl()) == 5 else 0
+  # fp8_v_quant_method: 0 per_block, 1 per_channel (codes of functional._QUANT_CODE)
+  p.fp8 = (1 | (2 if fp8_smooth_k else 0) | (4 if fp8_smooth_v else 0) | (8 if int(fp8_v_quant_method) == 1 else 0)) \
+      if int(_lib.ffpa_b200_get_backend_impl()) == 5 else 0
   p.softmax_scale = float(softmax_scale)
   p.dropout_p = float(dropout_p)
   p.philox_seed = int(philox_seed) & 0xFFFFFFFFFFFFFFFF

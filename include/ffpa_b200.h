@@ -72,7 +72,8 @@ typedef struct ffpa_fwd_params {
   int32_t causal;    /* 0 / 1 */
   int32_t fp8;       /* 0: fp16/bf16 MMA; bit 0: per-tile e4m3 quantised MMA (FFPA_IMPL_CUTE_TMA_FP8);
                         bit 1: smooth-K (quantise K - mean_seq(K), LSE corrected; the reference's default);
-                        bit 2: smooth-V (quantise V - mean_seq(V), mean added back to O) */
+                        bit 2: smooth-V (quantise V - mean_seq(V), mean added back to O);
+                        bit 3: per-channel V scales instead of per-128-row-block ones */
   float softmax_scale;
   float dropout_p;
   uint64_t philox_seed;

@@ -106,6 +106,35 @@ def test_fp8_smooth_v_removes_channel_mean_error():
   assert errs[True] < 0.5 * errs[False], errs
 
 
+def test_fp8_per_channel_v_scales_protect_small_channels():
+  """fp8_v_quant_method="per_channel" (reference knob): one scale per V channel, applied in the epilogue. With
+  channels of very different magnitude a per-block scale is set by the largest channel and the small channels lose
+  their precision; per-channel scales keep the error proportional to each channel's own magnitude."""
+  import ffpa_attn
+
+  q, k, v = _mk(1, 2, 2, 512, 768, 256, torch.bfloat16, seed=7)
+  gain = torch.ones(256)
+  # e4m3 is a floating-point format: a shared block scale only hurts channels more than ~2^15 below the largest one
+  # (they fall into the subnormals / flush to zero); every eighth channel is 1e5 x larger here, and the small
+  # channels carry an offset of 0.3 so that losing them is a bias the softmax average cannot hide
+  gain[::8] = 1.0e5
+  v = ((v.float() * 0.5 + 0.3) * gain.to(DEV)).to(torch.bfloat16)
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu())
+  small = (gain == 1.0).numpy()
+  errs = {}
+  for method in ("per_block", "per_channel"):
+    n0 = ffpa_attn._C.launch_count()
+    be = ffpa_attn.CUDABackend(enable_fp8=True, fp8_v_quant_method=method)
+    out = ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=be)
+    torch.cuda.synchronize()
+    assert ffpa_attn._C.launch_count() - n0 == 4 + (1 if method == "per_channel" else 0)
+    e = np.abs(out.float().cpu().numpy() - ref)
+    errs[method] = (float(e[..., small].max()), float(e[..., ~small].max()))
+  assert errs["per_channel"][0] < 0.25 * errs["per_block"][0], errs     # small channels: flushed before, kept now
+  assert errs["per_channel"][1] < 2.0 * errs["per_block"][1], errs       # large channels: no worse than noise
+  assert errs["per_channel"][0] < 8e-2, errs
+
+
 def test_fp8_lse_and_large_amplitude():
   import ffpa_attn
   import ffpa_attn.cuda as fc
