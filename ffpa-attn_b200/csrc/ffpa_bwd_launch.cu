@@ -146,6 +146,7 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
           s.dk = const_cast<void*>(off(a.dk, b * a.dk_stride[0] + hk0 * a.dk_stride[1]));
           s.dv = const_cast<void*>(off(a.dv, b * a.dv_stride[0] + hk0 * a.dv_stride[1]));
           s.lse = a.lse + ((int64_t)b * a.heads_q + hq0) * a.seqlen_q;
+          if (a.d_lse) s.d_lse = a.d_lse + ((int64_t)b * a.heads_q + hq0) * a.seqlen_q;
           if (int rc = launch_bwd_sm100(s, stream)) return rc;
         }
       return FFPA_OK;

@@ -685,7 +685,8 @@ __global__ void bwd_preprocess_kernel(const void* __restrict__ o, const void* __
                                       const float* __restrict__ lse, float* __restrict__ lse2,
                                       float* __restrict__ delta, int64_t os0, int64_t os1, int64_t os2,
                                       int64_t ds0, int64_t ds1, int64_t ds2, int B, int H, int Nq,
-                                      int nq_pad, int D, const int* __restrict__ cu_q, int total_q) {
+                                      int nq_pad, int D, const int* __restrict__ cu_q, int total_q,
+                                      const float* __restrict__ dlse) {
   const int warps_per_block = blockDim.x >> 5;
   const int64_t rowid = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int64_t total = (int64_t)B * H * nq_pad;
@@ -732,7 +733,8 @@ __global__ void bwd_preprocess_kernel(const void* __restrict__ o, const void* __
   if (lane == 0) {
     const float l = lse[lse_idx];
     lse2[rowid] = (l == -INFINITY) ? INFINITY : l * 1.4426950408889634f;
-    delta[rowid] = acc;
+    // dLSE: d lse_i / d s_ij = p_ij, so dS = P (dP - delta + dlse): fold it into delta
+    delta[rowid] = dlse != nullptr ? acc - dlse[lse_idx] : acc;
   }
 }
 
@@ -805,7 +807,7 @@ int launch_preprocess(const ffpa_bwd_params& a, float* lse2, float* delta, int n
   const int64_t blocks = (rows + wpb - 1) / wpb;
   bwd_preprocess_kernel<BF16><<<dim3((unsigned)blocks), dim3(wpb * 32), 0, stream>>>(
       a.o, a.d_o, a.lse, lse2, delta, a.o_stride[0], a.o_stride[1], a.o_stride[2], a.do_stride[0],
-      a.do_stride[1], a.do_stride[2], a.batch, a.heads_q, a.seqlen_q, nq_pad, a.head_dim, a.cu_seqlens_q, a.total_q);
+      a.do_stride[1], a.do_stride[2], a.batch, a.heads_q, a.seqlen_q, nq_pad, a.head_dim, a.cu_seqlens_q, a.total_q, a.d_lse);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "backward preprocess launch failed: %s", cudaGetErrorString(e));
   count_launch();

@@ -74,6 +74,7 @@ class _BwdParams(ctypes.Structure):
     ("d_bias", ctypes.c_void_p),
     ("cu_seqlens_q", ctypes.c_void_p), ("cu_seqlens_k", ctypes.c_void_p),
     ("total_q", ctypes.c_int32), ("total_k", ctypes.c_int32),
+    ("d_lse", ctypes.c_void_p),
   ]
 
 
@@ -279,7 +280,7 @@ def ffpa_attn_forward(Q, K, V, attn_bias, O, softmax_lse, stages, acc, causal, s
 
 def ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale,
                        attn_bias=None, dropout_p=0.0, philox_seed=0, philox_offset=0, d_bias=None,
-                       min_workspace=False) -> None:
+                       min_workspace=False, d_lse=None) -> None:
   """Positional signature of ffpa_api.cc:242-246 (a thrower in the reference); real here.
   Keyword extras replay what the forward applied: additive ``attn_bias``, dropout (same Philox
   seed/offset) and ``d_bias`` -- an fp32 [B, Hq, Nq, Nkv] buffer that receives dS per score."""
@@ -316,6 +317,10 @@ def ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, 
     p.d_bias = d_bias.data_ptr()
   else:
     p.d_bias = None
+  if d_lse is not None:
+    if d_lse.dtype != torch.float32 or not d_lse.is_contiguous() or d_lse.shape != softmax_lse.shape:
+      raise RuntimeError("ffpa_attn_backward: d_lse must be contiguous fp32 with the shape of softmax_lse")
+    p.d_lse = d_lse.data_ptr()
   with torch.cuda.device(Q.device):
     stream = torch.cuda.current_stream(Q.device).cuda_stream
     rc = _lib.ffpa_b200_bwd(ctypes.byref(p), ctypes.c_void_p(stream))
@@ -377,7 +382,7 @@ def ffpa_attn_varlen_forward(Q, K, V, O, softmax_lse, cu_seqlens_q, cu_seqlens_k
 
 
 def ffpa_attn_varlen_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, cu_seqlens_q, cu_seqlens_k,
-                              max_seqlen_q, max_seqlen_k, causal, softmax_scale) -> None:
+                              max_seqlen_q, max_seqlen_k, causal, softmax_scale, d_lse=None) -> None:
   """Packed variable-length backward (preprocess + dQ + dK + dV launches for the whole batch)."""
   _check_cuda(Q, K, V, O, dO, dQ, dK, dV, softmax_lse, cu_seqlens_q, cu_seqlens_k)
   _check_varlen(Q, K, V, cu_seqlens_q, cu_seqlens_k)
@@ -398,6 +403,10 @@ def ffpa_attn_varlen_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, cu_seqlen
   p.dtype = _dtype_code(Q)
   p.causal = int(causal)
   p.softmax_scale = float(softmax_scale)
+  if d_lse is not None:
+    if d_lse.dtype != torch.float32 or not d_lse.is_contiguous() or d_lse.shape != softmax_lse.shape:
+      raise RuntimeError("ffpa_attn varlen backward: d_lse must be contiguous fp32 [Hq, T_q]")
+    p.d_lse = d_lse.data_ptr()
   nbytes = int(_lib.ffpa_b200_bwd_workspace_bytes_min(p.batch, p.heads_q, p.heads_kv, p.seqlen_q, p.seqlen_kv, p.head_dim))
   ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=Q.device)
   p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes

@@ -170,23 +170,23 @@ def _varlen_fwd_cuda_fake(Q, K, V, cu_q, cu_k, max_q, max_k, causal, softmax_sca
 torch.library.define(
   f"{_OP_NAMESPACE}::_varlen_bwd_cuda",
   "(Tensor q, Tensor k, Tensor v, Tensor o, Tensor softmax_lse, Tensor d_o, Tensor cu_seqlens_q, Tensor cu_seqlens_k, "
-  "int max_seqlen_q, int max_seqlen_k, int causal, float softmax_scale) -> (Tensor dq, Tensor dk, Tensor dv)",
+  "int max_seqlen_q, int max_seqlen_k, int causal, float softmax_scale, Tensor? d_lse=None) -> (Tensor dq, Tensor dk, Tensor dv)",
 )
 
 
 @torch.library.impl(f"{_OP_NAMESPACE}::_varlen_bwd_cuda", "CUDA")
-def _varlen_bwd_cuda_torch_op(Q, K, V, O, softmax_lse, dO, cu_q, cu_k, max_q, max_k, causal, softmax_scale):
+def _varlen_bwd_cuda_torch_op(Q, K, V, O, softmax_lse, dO, cu_q, cu_k, max_q, max_k, causal, softmax_scale, d_lse=None):
   # tokens outside every sequence (none when cu_seqlens spans the tensors) keep a zero gradient
   dQ = torch.zeros_like(Q, memory_format=torch.contiguous_format)
   dK = torch.zeros_like(K, memory_format=torch.contiguous_format)
   dV = torch.zeros_like(V, memory_format=torch.contiguous_format)
   _cuda_ext.ffpa_attn_varlen_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, cu_q, cu_k, max_q, max_k,
-                                      causal, softmax_scale)
+                                      causal, softmax_scale, d_lse=d_lse)
   return dQ, dK, dV
 
 
 @torch.library.register_fake(f"{_OP_NAMESPACE}::_varlen_bwd_cuda")
-def _varlen_bwd_cuda_fake(Q, K, V, O, softmax_lse, dO, cu_q, cu_k, max_q, max_k, causal, softmax_scale):
+def _varlen_bwd_cuda_fake(Q, K, V, O, softmax_lse, dO, cu_q, cu_k, max_q, max_k, causal, softmax_scale, d_lse=None):
   return (torch.empty_like(Q, memory_format=torch.contiguous_format),
           torch.empty_like(K, memory_format=torch.contiguous_format),
           torch.empty_like(V, memory_format=torch.contiguous_format))

@@ -124,13 +124,17 @@ class _FFPAVarlenFunc(torch.autograd.Function):
     out, lse = torch.ops.ffpa_attn._varlen_fwd_cuda(qc, kc, vc, cu_q, cu_k, max_q, max_k, int(causal), scale)
     ctx.save_for_backward(qc, kc, vc, out, lse, cu_q, cu_k)
     ctx.args = (max_q, max_k, int(causal), scale)
-    ctx.mark_non_differentiable(lse)
+    ctx.set_materialize_grads(False)   # d_lse stays None unless the caller differentiates through the LSE
     return out, lse
 
   @staticmethod
-  def backward(ctx, d_o, _d_lse):
+  def backward(ctx, d_o, d_lse):
     q, k, v, out, lse, cu_q, cu_k = ctx.saved_tensors
     max_q, max_k, causal, scale = ctx.args
+    if d_o is None:
+      d_o = torch.zeros_like(out)
+    # the LSE output is differentiable (reference: cute/_bwd_preprocess.py:6-15): dS gains P * dLSE
+    d_lse = d_lse.float().contiguous() if d_lse is not None else None
     dq, dk, dv = torch.ops.ffpa_attn._varlen_bwd_cuda(q, k, v, out, lse, d_o.contiguous(), cu_q, cu_k,
-                                                     max_q, max_k, causal, scale)
+                                                     max_q, max_k, causal, scale, d_lse)
     return dq, dk, dv, None, None, None, None, None, None

@@ -129,6 +129,9 @@ typedef struct ffpa_bwd_params {
   const int32_t* cu_seqlens_q;
   const int32_t* cu_seqlens_k;
   int32_t total_q, total_k;
+  /* optional gradient of the loss w.r.t. the LSE output (same shape as lse; NULL = zero): dS gains P * dLSE,
+   * folded into delta by the preprocess kernel (reference: cute/_bwd_preprocess.py:6-15) */
+  const float* d_lse;
 } ffpa_bwd_params;
 
 /* replaces ffpa_attn_forward (/root/reference/csrc/cuffpa/ffpa_api.cc:86-239) */

@@ -63,10 +63,11 @@ int main(void) {
          offsetof(ffpa_fwd_params, philox_seed), offsetof(ffpa_fwd_params, philox_offset),
          offsetof(ffpa_fwd_params, workspace_bytes), offsetof(ffpa_fwd_params, cu_seqlens_q),
          offsetof(ffpa_fwd_params, total_k));
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ffpa_bwd_params), offsetof(ffpa_bwd_params, batch),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu ", sizeof(ffpa_bwd_params), offsetof(ffpa_bwd_params, batch),
          offsetof(ffpa_bwd_params, softmax_scale), offsetof(ffpa_bwd_params, workspace),
          offsetof(ffpa_bwd_params, bias_kind), offsetof(ffpa_bwd_params, d_bias),
          offsetof(ffpa_bwd_params, cu_seqlens_k), offsetof(ffpa_bwd_params, total_q));
+  printf("%zu\n", offsetof(ffpa_bwd_params, d_lse));
   return 0;
 }
 """
@@ -81,7 +82,7 @@ int main(void) {
           F.philox_seed.offset, F.philox_offset.offset, F.workspace_bytes.offset,
           F.cu_seqlens_q.offset, F.total_k.offset,
           ctypes.sizeof(B), B.batch.offset, B.softmax_scale.offset, B.workspace.offset,
-          B.bias_kind.offset, B.d_bias.offset, B.cu_seqlens_k.offset, B.total_q.offset]
+          B.bias_kind.offset, B.d_bias.offset, B.cu_seqlens_k.offset, B.total_q.offset, B.d_lse.offset]
   assert [int(x) for x in out] == want
 
 

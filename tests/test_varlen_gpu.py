@@ -164,3 +164,39 @@ def test_host_buffer_entry_matches_device_call_and_oracle(causal, Hkv, chunks):
   # pageable inputs and an allocated output also work
   out2 = ffpa_attn.ffpa_attn_host_func(hq.clone(), hk.clone(), hv.clone(), is_causal=causal, enable_gqa=Hq != Hkv)
   assert torch.equal(out2, ho)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_varlen_lse_output_is_differentiable(causal):
+  """The LSE returned by the packed entry carries a gradient (reference: cute/_bwd_preprocess.py:6-15):
+  dS gains P * dLSE, folded into delta by the preprocess kernel. Checked against fp32 autograd."""
+  import ffpa_attn
+
+  lens = [200, 77]
+  q, k, v, cq, ck = _pack(lens, lens, 2, 2, 128, torch.bfloat16, seed=9)
+  d_o = torch.randn_like(q)
+  w = torch.randn(2, q.size(0), device=DEV)
+  qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+  out, lse = ffpa_attn.ffpa_attn_varlen_func(qg, kg, vg, cq, ck, max(lens), max(lens), causal=causal, return_lse=True)
+  ((out.float() * d_o.float()).sum() + (lse * w).sum()).backward()
+  torch.cuda.synchronize()
+  cql = cq.tolist()
+  for b in range(len(lens)):
+    s = slice(cql[b], cql[b + 1])
+    q32, k32, v32 = (t[s].float().transpose(0, 1).detach().requires_grad_(True) for t in (q, k, v))   # [H, n, D]
+    sc = (q32 @ k32.transpose(-1, -2)) * 128 ** -0.5
+    if causal:
+      n = sc.size(-1)
+      sc = sc.masked_fill(~torch.ones(n, n, dtype=torch.bool, device=DEV).tril(), float("-inf"))
+    ref_lse = torch.logsumexp(sc, dim=-1)
+    ref_out = torch.softmax(sc, dim=-1) @ v32
+    ((ref_out * d_o[s].float().transpose(0, 1)).sum() + (ref_lse * w[:, s]).sum()).backward()
+    assert (lse[:, s] - ref_lse).abs().max().item() < 2e-3
+    for got, want, name in ((qg.grad[s], q32.grad, "dQ"), (kg.grad[s], k32.grad, "dK"), (vg.grad[s], v32.grad, "dV")):
+      err = (got.float().transpose(0, 1) - want).abs().max().item()
+      assert err < 5e-2 * max(1.0, want.abs().max().item()), f"{name} seq {b}: {err}"
+  # LSE alone (no gradient through out) also works: d_o is materialised as zeros
+  qg2 = q.clone().requires_grad_(True)
+  _, lse2 = ffpa_attn.ffpa_attn_varlen_func(qg2, k, v, cq, ck, max(lens), max(lens), causal=causal, return_lse=True)
+  (lse2 * w).sum().backward()
+  assert torch.isfinite(qg2.grad.float()).all() and qg2.grad.float().abs().max().item() > 0
