@@ -321,3 +321,19 @@ def test_fp8_hybrid_auto_resolution():
   with pytest.raises(RuntimeError, match="no CPU"):
     meta.normalize_inputs(q, k, v, None, 0.0, True, None, False)
   assert meta.forward_meta.fp8_hybrid is False
+
+
+def test_varlen_fake_ops_registered_for_compile():
+  """torch.compile sees the packed ops through their fake (shape-only) implementations."""
+  import ffpa_attn  # noqa: F401
+
+  q = torch.empty(48, 4, 128, dtype=torch.float16, device="meta")
+  k = torch.empty(64, 2, 128, dtype=torch.float16, device="meta")
+  cu = torch.empty(3, dtype=torch.int32, device="meta")
+  o, lse = torch.ops.ffpa_attn._varlen_fwd_cuda(q, k, k, cu, cu, 32, 40, 1, 0.1)
+  assert o.shape == q.shape and o.dtype == q.dtype
+  assert lse.shape == (4, 48) and lse.dtype == torch.float32
+  dq, dk, dv = torch.ops.ffpa_attn._varlen_bwd_cuda(q, k, k, o, lse, o, cu, cu, 32, 40, 1, 0.1, None)
+  assert dq.shape == q.shape and dk.shape == k.shape and dv.shape == k.shape
+  dq, dk, dv = torch.ops.ffpa_attn._varlen_bwd_cuda(q, k, k, o, lse, o, cu, cu, 32, 40, 1, 0.1, lse)
+  assert dq.shape == q.shape
