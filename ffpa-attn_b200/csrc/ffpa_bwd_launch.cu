@@ -47,37 +47,6 @@ static bool may_split_kv(int batch, int heads_kv, int seqlen_kv) {
   return kv_items < 8ll * (sm_count() / 2);
 }
 
-// Stash path (ffpa_bwd_gemm_sm100.cuh): two 16-bit [B, Hq, nq_pad, nk_pad] score buffers (P_drop and dS).
-// It pays when a GEMM pass over the head dim costs more than moving the N x N tile through HBM: head dims
-// >= 384 (above 512 the dQ kernel stores on the first of its two slab passes and the GEMM-only kernel runs one
-// pass per 512-wide output slab). FFPA_BWD_STASH=0 disables it; FFPA_BWD_STASH_MAX_GB (default 20) bounds both
-// buffers together: a larger problem is cut into (batch element, KV-head range) chunks that run one after the
-// other through the same buffers; if not even one KV head fits, the three recompute kernels run (O(N) memory).
-struct StashPlan {
-  uint64_t one = 0;     // bytes of ONE score buffer (of a chunk when chunked); 0 = path does not apply
-  int chunk_hkv = 0;    // KV heads per chunk
-  bool chunked = false;
-};
-static StashPlan stash_plan(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
-  StashPlan pl;
-  if (head_dim < 384 || head_dim > 1024 || heads_kv <= 0) return pl;
-  const char* e = getenv("FFPA_BWD_STASH");
-  if (e && e[0] == '0') return pl;
-  const char* g = getenv("FFPA_BWD_STASH_MAX_GB");
-  const double cap = (g ? atof(g) : 20.0) * 1073741824.0;
-  const uint64_t nq_pad = ((uint64_t)seqlen_q + 127) / 128 * 128, nk_pad = ((uint64_t)seqlen_kv + 255) / 256 * 256;
-  const int group = heads_q / heads_kv;
-  const uint64_t per_hkv = (uint64_t)group * nq_pad * nk_pad * 2;   // multiple of 256 bytes
-  const uint64_t total = (uint64_t)batch * heads_kv * per_hkv;
-  if (2.0 * (double)total <= cap) { pl.one = total; pl.chunk_hkv = heads_kv; return pl; }
-  int hc = (int)(cap / (2.0 * (double)per_hkv));
-  hc = hc > heads_kv ? heads_kv : hc;
-  // a chunk must still fill the machine: query row tiles x query heads of the chunk
-  if (hc < 1 || (int64_t)hc * group * (int64_t)(nq_pad / 128) < sm_count() / 2) return pl;
-  pl.one = (uint64_t)hc * per_hkv; pl.chunk_hkv = hc; pl.chunked = true;
-  return pl;
-}
-
 uint64_t bwd_workspace_bytes_min(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
   const uint64_t nq_pad = ((uint64_t)seqlen_q + 127) / 128 * 128;
   uint64_t total = align256(2ull * batch * heads_q * nq_pad * sizeof(float));
@@ -86,15 +55,53 @@ uint64_t bwd_workspace_bytes_min(int batch, int heads_q, int heads_kv, int seqle
   return total;
 }
 
-uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim) {
-  const uint64_t whole = bwd_workspace_bytes_min(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
-  const StashPlan pl = stash_plan(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
-  if (pl.one == 0) return whole;
-  if (!pl.chunked) return whole + 2 * pl.one;
-  // chunked: every chunk is a self-contained sub-problem (batch 1, chunk_hkv KV heads) in the same scratch
+// Stash path (ffpa_bwd_gemm_sm100.cuh): two 16-bit [B, Hq, nq_pad, nk_pad] score buffers (P_drop and dS).
+// It pays when a GEMM pass over the head dim costs more than moving the N x N tile through HBM: head dims
+// >= 384 (above 512 the dQ kernel stores on the first of its two slab passes and the GEMM-only kernel runs one
+// pass per 512-wide output slab). The plan is a pure function of the workspace bytes on offer (`avail`): at
+// sizing time that is the caller's cap (the torch binding derives it from free device memory), at launch the
+// bytes actually granted -- so any workspace >= the minimum is valid and more memory means fewer GEMM passes.
+// A problem whose buffers do not fit is cut into (batch element, KV-head range) chunks that run one after the
+// other through the same buffers; if not even a machine-filling chunk fits, the three recompute kernels run
+// (O(N) memory). FFPA_BWD_STASH=0 disables the path; how much memory to offer is the binder's policy
+// (csrc/ffpa_torch_binding.cpp: at most half of the free memory, FFPA_BWD_STASH_MAX_GB as an upper bound).
+struct StashPlan {
+  uint64_t one = 0;     // bytes of ONE score buffer (of a chunk when chunked); 0 = path does not apply
+  int chunk_hkv = 0;    // KV heads per chunk
+  bool chunked = false;
+  uint64_t need = 0;    // workspace bytes this plan needs (minimum scratch included)
+};
+static StashPlan stash_plan(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim, uint64_t avail) {
+  StashPlan pl;
+  if (head_dim < 384 || head_dim > 1024 || heads_kv <= 0) return pl;
+  if (env_off("FFPA_BWD_STASH")) return pl;
+  const uint64_t nq_pad = ((uint64_t)seqlen_q + 127) / 128 * 128, nk_pad = ((uint64_t)seqlen_kv + 255) / 256 * 256;
   const int group = heads_q / heads_kv;
-  const uint64_t sub = bwd_workspace_bytes_min(1, pl.chunk_hkv * group, pl.chunk_hkv, seqlen_q, seqlen_kv, head_dim) + 2 * pl.one;
-  return sub > whole ? sub : whole;
+  const uint64_t per_hkv = (uint64_t)group * nq_pad * nk_pad * 2;   // multiple of 256 bytes
+  const uint64_t total = (uint64_t)batch * heads_kv * per_hkv;
+  const uint64_t whole = bwd_workspace_bytes_min(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
+  if (whole + 2 * total <= avail) {
+    pl.one = total; pl.chunk_hkv = heads_kv; pl.need = whole + 2 * total;
+    return pl;
+  }
+  // largest KV-head count whose sub-problem (batch 1) fits; a chunk must still fill the machine
+  for (int hc = heads_kv; hc >= 1; --hc) {
+    const uint64_t sub = bwd_workspace_bytes_min(1, hc * group, hc, seqlen_q, seqlen_kv, head_dim) + 2 * hc * per_hkv;
+    if (sub > avail) continue;
+    if ((int64_t)hc * group * (int64_t)(nq_pad / 128) < sm_count() / 2) break;
+    if (hc == heads_kv && batch == 1) break;   // would be the unchunked plan, which did not fit
+    pl.one = (uint64_t)hc * per_hkv; pl.chunk_hkv = hc; pl.chunked = true;
+    pl.need = sub > whole ? sub : whole;
+    return pl;
+  }
+  return pl;
+}
+
+uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim, uint64_t cap_bytes) {
+  const uint64_t whole = bwd_workspace_bytes_min(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim);
+  if (cap_bytes <= whole) return whole;
+  const StashPlan pl = stash_plan(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim, cap_bytes);
+  return pl.one == 0 ? whole : pl.need;
 }
 
 template <bool BF16>
@@ -123,13 +130,15 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   const int nqk = D > 512 ? (D + 127) / 128 * 2 : (D + 63) / 64;
   const int n_pass = D > 512 ? 2 : 1;
   const int nq_pad = (a.seqlen_q + 127) / 128 * 128;
-  const StashPlan plan = a.cu_seqlens_q ? StashPlan{} : stash_plan(a.batch, a.heads_q, a.heads_kv, a.seqlen_q, a.seqlen_kv, D);
+  // plan from the bytes actually granted (any size >= the minimum is valid; more memory = fewer GEMM passes)
+  const StashPlan plan = (a.cu_seqlens_q || !a.workspace)
+                             ? StashPlan{}
+                             : stash_plan(a.batch, a.heads_q, a.heads_kv, a.seqlen_q, a.seqlen_kv, D, a.workspace_bytes);
   if (plan.chunked && a.bias_kind == FFPA_BIAS_NONE && !(a.dropout_p > 0.f) && a.d_bias == nullptr) {
     // stash buffers bounded by FFPA_BWD_STASH_MAX_GB: run (batch element, KV-head range) chunks one after the other
     // through the same scratch (stream order serialises them); each chunk is an ordinary dense sub-problem
     const int group = a.heads_q / a.heads_kv;
-    const uint64_t sub_need = bwd_workspace_bytes_min(1, plan.chunk_hkv * group, plan.chunk_hkv, a.seqlen_q, a.seqlen_kv, D) + 2 * plan.one;
-    if (a.workspace && a.workspace_bytes >= sub_need) {
+    {
       auto off = [](const void* p, int64_t elems) { return static_cast<const void*>(static_cast<const uint8_t*>(p) + 2 * elems); };
       for (int b = 0; b < a.batch; ++b)
         for (int hk0 = 0; hk0 < a.heads_kv; hk0 += plan.chunk_hkv) {
@@ -195,6 +204,21 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   for (int i = 0; i < 4; ++i) kp.bias_stride[i] = a.bias_stride[i];
   kp.dropout_p = a.dropout_p; kp.philox_seed = a.philox_seed; kp.philox_offset = a.philox_offset;
   kp.dbias = a.d_bias;
+  for (int i = 0; i < 4; ++i) kp.dbias_stride[i] = a.d_bias_stride[i];
+  if (a.d_bias) {
+    // the dQ kernel accumulates into the bias-shaped buffer (atomics wherever a dim is reduced): start from zero
+    const int ext[4] = {a.batch, a.heads_q, a.seqlen_q, a.seqlen_kv};
+    bool reduced = false;
+    uint64_t elems = 1;
+    for (int i = 0; i < 4; ++i) {
+      if (a.d_bias_stride[i] == 0) reduced = reduced || ext[i] > 1;
+      else elems *= (uint64_t)ext[i];
+    }
+    if (reduced) {
+      cudaError_t e = cudaMemsetAsync(a.d_bias, 0, elems * sizeof(float), stream);
+      if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaMemsetAsync(d_bias): %s", cudaGetErrorString(e));
+    }
+  }
   kp.cu_q = a.cu_seqlens_q;
   kp.cu_k = a.cu_seqlens_k;
   kp.total_q = a.total_q; kp.total_k = a.total_k;

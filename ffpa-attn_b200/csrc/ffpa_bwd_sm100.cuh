@@ -535,6 +535,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         // element jj: dQ kind (q = grow, key = col), dK/dV kinds (q = col, key = grow).
         const int hq_cur = (KIND == kKindDQ) ? hs : hs * group + gi;
         const float inv_keep = GENERAL ? 1.f / (1.f - p.dropout_p) : 1.f;
+        float dsv[(GENERAL && KIND == kKindDQ) ? 32 : 1];   // fp32 dS of this thread's 32 columns (dBias)
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float e[2], pv[2] = {0.f, 0.f};
@@ -558,7 +559,7 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
               const bool inb = qi < seq_q && ki < seq_kv;
               if (p.bias_kind != 0 && inb) {
                 const int64_t bo = (int64_t)b * p.bias_stride[0] + (int64_t)hq_cur * p.bias_stride[1] +
-                                   (int64_t)qi * p.bias_stride[2] + ki;
+                                   (int64_t)qi * p.bias_stride[2] + (int64_t)ki * p.bias_stride[3];
                 float bv;
                 if (p.bias_kind == 1) bv = reinterpret_cast<const float*>(p.bias)[bo];
                 else if (BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[bo]);
@@ -581,16 +582,50 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
               const float ds = pe * (__uint_as_float(dr[jj]) * mult - dl);
               e[u] = ds;
               if (KIND == kKindDQ) pv[u] = pe * mult;   // P_drop (what dV consumes), only used by the stash path
-              if constexpr (GENERAL && KIND == kKindDQ) {
-                if (p.dbias != nullptr && itm.pass == 0 && qi < seq_q && ki < seq_kv)
-                  p.dbias[(((int64_t)b * p.heads_q + hq_cur) * p.seqlen_q + qi) * (int64_t)p.seqlen_kv + ki] = ds;
-              }
+              if constexpr (GENERAL && KIND == kKindDQ) dsv[jj] = ds;
             } else {
               e[u] = pe * mult;
             }
           }
           pk[j >> 1] = BF16 ? ptx::pack_bf16x2(e[0], e[1]) : ptx::pack_f16x2(e[0], e[1]);
           if (KIND == kKindDQ) pp[j >> 1] = BF16 ? ptx::pack_bf16x2(pv[0], pv[1]) : ptx::pack_f16x2(pv[0], pv[1]);
+        }
+        // dBias = dS reduced over the dims the bias broadcasts over, accumulated straight into the bias-shaped
+        // fp32 buffer: a bias without a query dim is first summed over the warp's 32 rows (butterfly
+        // reduce-scatter, 31 shuffles: lane L ends up with column col0 + L), then one atomic per column.
+        if constexpr (GENERAL && KIND == kKindDQ) {
+          if (p.dbias != nullptr && itm.pass == 0) {
+            float* dbase = p.dbias + (int64_t)b * p.dbias_stride[0] + (int64_t)hq_cur * p.dbias_stride[1];
+            const bool red_bh = (p.dbias_stride[0] == 0 && p.batch > 1) || (p.dbias_stride[1] == 0 && p.heads_q > 1);
+            if (p.dbias_stride[2] != 0 || seq_q == 1) {
+              const bool red = red_bh || (p.dbias_stride[3] == 0 && seq_kv > 1);
+              if (grow < seq_q) {
+                float* drow = dbase + (int64_t)grow * p.dbias_stride[2];
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                  const int ki = col0 + jj;
+                  if (ki < seq_kv) {
+                    if (red) atomicAdd(drow + (int64_t)ki * p.dbias_stride[3], dsv[jj]);
+                    else drow[(int64_t)ki * p.dbias_stride[3]] = dsv[jj];
+                  }
+                }
+              }
+            } else {
+              const uint32_t ln = threadIdx.x & 31;
+#pragma unroll
+              for (int w = 16; w >= 1; w >>= 1) {
+                const bool hi = (ln & w) != 0;
+#pragma unroll
+                for (int i2 = 0; i2 < w; ++i2) {
+                  const float keep = hi ? dsv[i2 + w] : dsv[i2];
+                  const float send = hi ? dsv[i2] : dsv[i2 + w];
+                  dsv[i2] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+                }
+              }
+              const int ki = col0 + (int)ln;
+              if (ki < seq_kv) atomicAdd(dbase + (int64_t)ki * p.dbias_stride[3], dsv[0]);
+            }
+          }
         }
         // stash path: T single-buffered (buffer 0), buffer 1 stages P_drop; both leave through the store warp
         const uint32_t tb = stash ? 0u : sbuf;

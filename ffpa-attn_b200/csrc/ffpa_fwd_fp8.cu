@@ -1,5 +1,5 @@
 // FP8 forward: host launcher (workspace carving, fused quantisation pre-pass, tensor maps,
-// dispatch). Entry: launch_fwd_fp8_sm100 (called from ffpa_b200_fwd when params.fp8 != 0).
+// dispatch). Entry: launch_fwd_fp8_sm100 (called from ffpa_b200_fwd when the call resolves to FFPA_IMPL_CUTE_TMA_FP8).
 #include "ffpa_fwd_fp8_sm100.cuh"
 
 namespace ffpa {
@@ -55,7 +55,7 @@ static int dispatch_nb(int nb, const CUtensorMap& mq, const CUtensorMap& mk, con
   }
 }
 
-int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
+int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, int fp8_bits, cudaStream_t stream) {
   const int B = a.batch, Hq = a.heads_q, Hkv = a.heads_kv, Nq = a.seqlen_q, Nkv = a.seqlen_kv, D = a.head_dim;
   if (D > 512) return set_error(FFPA_ERR_UNSUPPORTED, "FP8 forward supports head_dim <= 512 (got %d)", D);
   if (a.bias_kind != FFPA_BIAS_NONE || a.dropout_p > 0.f)
@@ -87,9 +87,9 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   qa.batch = B; qa.head_dim = D; qa.dpad = L.dpad;
   cudaError_t e = cudaMemsetAsync(qa.vref, 0, (size_t)B * Hkv * 4, stream);
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-  // smooth-K (a.fp8 bit 1; the reference's default, functional.py:246): quantise K - mean_seq(K) and shift
+  // smooth-K (fp8_bits bit 1; the reference's default, functional.py:246): quantise K - mean_seq(K) and shift
   // the LSE back by scale * q . mean
-  const bool smooth_k = (a.fp8 & 2) != 0;
+  const bool smooth_k = (fp8_bits & 2) != 0;
   float* ksum = reinterpret_cast<float*>(ws + L.off_ksum);
   float* qkm = reinterpret_cast<float*>(ws + L.off_qkm);
   qa.ksum = nullptr;
@@ -113,8 +113,8 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
     count_launch();
     qa.ksum = ksum;
   }
-  // smooth-V (a.fp8 bit 2; reference knob fp8_smooth_v): quantise V - mean_seq(V), add the mean back to O
-  const bool smooth_v = (a.fp8 & 4) != 0;
+  // smooth-V (fp8_bits bit 2; reference knob fp8_smooth_v): quantise V - mean_seq(V), add the mean back to O
+  const bool smooth_v = (fp8_bits & 4) != 0;
   float* vsum = reinterpret_cast<float*>(ws + L.off_vsum);
   qa.vsum = nullptr;
   if (smooth_v) {
@@ -131,8 +131,8 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
     count_launch();
     qa.vsum = vsum;
   }
-  // per-channel V scales (a.fp8 bit 3; reference knob fp8_v_quant_method="per_channel")
-  const bool v_per_channel = (a.fp8 & 8) != 0;
+  // per-channel V scales (fp8_bits bit 3; reference knob fp8_v_quant_method="per_channel")
+  const bool v_per_channel = (fp8_bits & 8) != 0;
   float* vamax = reinterpret_cast<float*>(ws + L.off_vamax);
   qa.vamax = nullptr;
   if (v_per_channel) {
@@ -164,6 +164,7 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
 
   fp8::Fp8KernelParams kp{};
   kp.o = a.o; kp.lse = a.lse;
+  kp.lse_bh_stride = a.lse_bh_stride > 0 ? a.lse_bh_stride : Nq;
   for (int i = 0; i < 3; ++i) kp.o_stride[i] = a.o_stride[i];
   kp.qs = qa.scale[0]; kp.ks = qa.scale[1]; kp.vs = qa.scale[2]; kp.vref = qa.vref;
   kp.qkm = smooth_k ? qkm : nullptr;

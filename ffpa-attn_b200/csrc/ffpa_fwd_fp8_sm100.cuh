@@ -34,6 +34,7 @@ constexpr float kPScale = 28.0f;         // 448 / 2^kLazyThreshold
 struct Fp8KernelParams {
   void* o;
   float* lse;
+  int64_t lse_bh_stride;
   int64_t o_stride[3];
   const float* qs;     // [B, Hq,  TQ]
   const float* ks;     // [B, Hkv, TK]
@@ -493,7 +494,7 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           const int64_t ridx = ((int64_t)b * p.heads_q + h) * p.seqlen_q + gq;
           const float corr = p.qkm != nullptr ? p.qkm[ridx] * (p.scale_log2 * 0.6931471805599453f) : 0.f;
           const float lse = (l_tot > 0.f) ? (m_fin + log2f(l_tot)) * 0.6931471805599453f + corr : NEG_INF;
-          p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
+          p.lse[((int64_t)b * p.heads_q + h) * p.lse_bh_stride + gq] = lse;
         }
         ptx::tc_fence_before();
         // xl is reused by the next item: all four writers must be past their reads first

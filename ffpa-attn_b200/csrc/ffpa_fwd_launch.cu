@@ -24,10 +24,10 @@ extern template int launch_fwd_replay<false>(const CUtensorMap&, const CUtensorM
 }  // namespace replay
 
 template <bool BF16>
-int launch_merge_splits(const float* part_o, const float* part_lse, void* o, float* lse, const int64_t* ostride, int B,
-                        int H, int Nq, int D, int S, cudaStream_t stream);
-extern template int launch_merge_splits<true>(const float*, const float*, void*, float*, const int64_t*, int, int, int, int, int, cudaStream_t);
-extern template int launch_merge_splits<false>(const float*, const float*, void*, float*, const int64_t*, int, int, int, int, int, cudaStream_t);
+int launch_merge_splits(const float* part_o, const float* part_lse, void* o, float* lse, int64_t lse_bh_stride,
+                        const int64_t* ostride, int B, int H, int Nq, int D, int S, cudaStream_t stream);
+extern template int launch_merge_splits<true>(const float*, const float*, void*, float*, int64_t, const int64_t*, int, int, int, int, int, cudaStream_t);
+extern template int launch_merge_splits<false>(const float*, const float*, void*, float*, int64_t, const int64_t*, int, int, int, int, int, cudaStream_t);
 
 // KV splits for decode-like shapes: few query tiles (items) and a long KV sequence leave most of the 74
 // clusters idle and one cluster streaming all of K/V of a head; splitting the KV range restores the
@@ -54,10 +54,8 @@ static ReplayPlan replay_plan(int batch, int heads_q, int seqlen_q, int seqlen_k
   ReplayPlan pl;
   const int nqk = (head_dim + 63) / 64, dvp = ((nqk * 64 + 127) / 128) * 128;
   if (dvp <= 768) return pl;
-  const char* e = getenv("FFPA_FWD_REPLAY");
-  if (e && e[0] == '0') return pl;
-  const char* g = getenv("FFPA_FWD_REPLAY_MAX_GB");
-  const double cap = (g ? atof(g) : 20.0) * 1073741824.0;
+  if (env_off("FFPA_FWD_REPLAY")) return pl;
+  const double cap = env_gb("FFPA_FWD_REPLAY_MAX_GB", 20.0) * 1073741824.0;
   const uint64_t bh = (uint64_t)batch * heads_q;
   const int n_mt_even = (((seqlen_q + 127) / 128) + 1) & ~1, nk_pad = (seqlen_kv + 255) / 256 * 256;
   const uint64_t p_bytes = bh * n_mt_even * 128ull * nk_pad * 2;
@@ -66,6 +64,11 @@ static ReplayPlan replay_plan(int batch, int heads_q, int seqlen_q, int seqlen_k
   if ((double)(p_bytes + f_bytes + inv_bytes) > cap) return pl;
   pl.p_bytes = p_bytes; pl.f_bytes = f_bytes; pl.inv_bytes = inv_bytes; pl.n_mt_even = n_mt_even; pl.nk_pad = nk_pad;
   return pl;
+}
+
+uint64_t fwd_replay_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
+  const ReplayPlan rp = replay_plan(batch, heads_q, seqlen_q, seqlen_kv, head_dim);
+  return rp.total() > 0 ? rp.total() + 256 : 0;
 }
 
 uint64_t fwd_split_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
@@ -104,6 +107,7 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   FwdKernelParams kp{};
   kp.o = a.o;
   kp.lse = a.lse;
+  kp.lse_bh_stride = a.lse_bh_stride > 0 ? a.lse_bh_stride : a.seqlen_q;
   kp.bias = a.bias;
   for (int i = 0; i < 3; ++i) kp.o_stride[i] = a.o_stride[i];
   for (int i = 0; i < 4; ++i) kp.bias_stride[i] = a.bias_stride[i];
@@ -206,8 +210,8 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   }
   if (kp.kv_splits == 1) return rc;
   return (a.dtype == FFPA_DTYPE_BF16)
-             ? launch_merge_splits<true>(kp.part_o, kp.part_lse, a.o, a.lse, a.o_stride, a.batch, a.heads_q, a.seqlen_q, D, kp.kv_splits, stream)
-             : launch_merge_splits<false>(kp.part_o, kp.part_lse, a.o, a.lse, a.o_stride, a.batch, a.heads_q, a.seqlen_q, D, kp.kv_splits, stream);
+             ? launch_merge_splits<true>(kp.part_o, kp.part_lse, a.o, a.lse, kp.lse_bh_stride, a.o_stride, a.batch, a.heads_q, a.seqlen_q, D, kp.kv_splits, stream)
+             : launch_merge_splits<false>(kp.part_o, kp.part_lse, a.o, a.lse, kp.lse_bh_stride, a.o_stride, a.batch, a.heads_q, a.seqlen_q, D, kp.kv_splits, stream);
 }
 
 }  // namespace ffpa

@@ -537,9 +537,10 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               const int key = key0 + j;
               float bv = 0.f;
               if (key < seq_kv) {
-                if (p.bias_kind == 1) bv = reinterpret_cast<const float*>(p.bias)[boff + key];
-                else if (BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[boff + key]);
-                else bv = __half2float(reinterpret_cast<const __half*>(p.bias)[boff + key]);
+                const int64_t bi = boff + (int64_t)key * p.bias_stride[3];   // k-stride 1, or 0 for a [.., 1] bias
+                if (p.bias_kind == 1) bv = reinterpret_cast<const float*>(p.bias)[bi];
+                else if (BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[bi]);
+                else bv = __half2float(reinterpret_cast<const __half*>(p.bias)[bi]);
               }
               x[j] = fmaf(__uint_as_float(sr[j]), p.scale_log2, bv * 1.4426950408889634f);
             }
@@ -793,7 +794,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const float lse = (l_tot > 0.f) ? (m * mul + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
           if (p.kv_splits > 1) p.part_lse[(((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq] = lse;
           else if (p.cu_q != nullptr) p.lse[(int64_t)h * p.total_q + fi.qoff + gq] = lse;   // [Hq, total_q]
-          else p.lse[((int64_t)b * p.heads_q + h) * p.seqlen_q + gq] = lse;
+          else p.lse[((int64_t)b * p.heads_q + h) * p.lse_bh_stride + gq] = lse;
         }
         ptx::tc_fence_before();
       }
@@ -812,8 +813,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 template <bool BF16>
 __global__ void merge_splits_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
-                                    void* __restrict__ o, float* __restrict__ lse, int64_t os0, int64_t os1, int64_t os2,
-                                    int B, int H, int Nq, int D, int S) {
+                                    void* __restrict__ o, float* __restrict__ lse, int64_t lse_bh_stride, int64_t os0,
+                                    int64_t os1, int64_t os2, int B, int H, int Nq, int D, int S) {
   const int64_t rowid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t rows = (int64_t)B * H * Nq;
   if (rowid >= rows) return;
@@ -842,16 +843,16 @@ __global__ void merge_splits_kernel(const float* __restrict__ part_o, const floa
     }
     *reinterpret_cast<uint32_t*>(orow + 2 * d) = BF16 ? ptx::pack_bf16x2(a0, a1) : ptx::pack_f16x2(a0, a1);
   }
-  if (lse != nullptr && lane == 0) lse[rowid] = den > 0.f ? mx + __logf(den) : -INFINITY;
+  if (lse != nullptr && lane == 0) lse[((int64_t)b * H + h) * lse_bh_stride + q] = den > 0.f ? mx + __logf(den) : -INFINITY;
 }
 
 template <bool BF16>
-int launch_merge_splits(const float* part_o, const float* part_lse, void* o, float* lse, const int64_t* ostride, int B,
-                        int H, int Nq, int D, int S, cudaStream_t stream) {
+int launch_merge_splits(const float* part_o, const float* part_lse, void* o, float* lse, int64_t lse_bh_stride,
+                        const int64_t* ostride, int B, int H, int Nq, int D, int S, cudaStream_t stream) {
   const int64_t rows = (int64_t)B * H * Nq;
   const int wpb = 4;
   merge_splits_kernel<BF16><<<dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream>>>(
-      part_o, part_lse, o, lse, ostride[0], ostride[1], ostride[2], B, H, Nq, D, S);
+      part_o, part_lse, o, lse, lse_bh_stride, ostride[0], ostride[1], ostride[2], B, H, Nq, D, S);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "split merge launch failed: %s", cudaGetErrorString(e));
   count_launch();

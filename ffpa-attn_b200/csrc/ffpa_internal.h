@@ -10,6 +10,7 @@ namespace ffpa {
 struct FwdKernelParams {
   void* o;
   float* lse;
+  int64_t lse_bh_stride;   // elements between the LSE rows of consecutive (b, h) pairs (dense layout)
   const void* bias;
   int64_t o_stride[3];     // (b, h, n) in elements
   int64_t bias_stride[4];  // (b, h, q, k) in elements
@@ -74,7 +75,8 @@ struct BwdKernelParams {
   int bias_kind;
   float dropout_p;
   uint64_t philox_seed, philox_offset;
-  float* dbias;
+  float* dbias;             // fp32, bias-shaped (dbias_stride 0 on the dims the bias broadcasts over)
+  int64_t dbias_stride[4];
   // scheduling: optional balanced table (as in the forward) and chunked items with fp32 atomics
   const int* sched;
   int sched_stride;
@@ -116,12 +118,17 @@ int sm_count();
 
 int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream);
 int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream);
-int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, cudaStream_t stream);
+// fp8_bits: 1 enable | 2 smooth-K | 4 smooth-V | 8 per-channel V scales
+int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, int fp8_bits, cudaStream_t stream);
 int fwd_kv_splits(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim);  // 1 = no split
 uint64_t fwd_split_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim);
 uint64_t fwd_fp8_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim);
+uint64_t fwd_replay_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim);
+// recommended backward scratch not above max(cap, minimum): adds the stash buffers (chunked when needed)
 uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv,
-                             int head_dim);
+                             int head_dim, uint64_t cap_bytes);
+double env_gb(const char* name, double dflt);   // cached getenv (read once per process)
+bool env_off(const char* name);                 // cached: variable set to a value starting with '0'
 uint64_t bwd_workspace_bytes_min(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv,
                                  int head_dim);
 

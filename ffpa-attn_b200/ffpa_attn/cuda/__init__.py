@@ -1,14 +1,21 @@
 """CUDA backend shim: registers ``torch.ops.ffpa_attn._fwd_cuda`` (and ``_bwd_cuda``) on top of
-the native binding, with the reference's op schema so ``torch.compile`` sees the same op
+the native binding ``ffpa_attn._C`` (a real PyTorch C++ extension, csrc/ffpa_torch_binding.cpp, with the
+reference module's pybind surface), with the reference's op schema so ``torch.compile`` sees the same op
 (/root/reference/src/ffpa_attn/cuda/__init__.py:28-35, 57-171; wrappers _ffpa_fwd.py:6-62,
-_ffpa_bwd.py:6-26).  The only backend behind the op is the sm_100a kernel family."""
+_ffpa_bwd.py:6-26).  The only backend behind the op is the sm_100a kernel family; a missing extension is an
+ImportError, never a fallback."""
 from __future__ import annotations
 
 import enum
 
 import torch
 
-from .. import _C as _cuda_ext
+try:
+  from .. import _C as _cuda_ext
+except ImportError as exc:  # no CPU / Triton / SDPA route exists: fail loudly
+  raise ImportError(
+    "ffpa_attn._C (the sm_100a PyTorch extension) is not built. Run `python -c 'import __graft_entry__ as g; "
+    f"g.build()'` (or `make -C ffpa-attn_b200/csrc`). There is no fallback backend. Original error: {exc}") from exc
 
 CUDA_FWD_AVAILABLE = _cuda_ext.CUDA_FWD_AVAILABLE
 CUDA_AVAILABLE = _cuda_ext.CUDA_AVAILABLE
@@ -35,6 +42,11 @@ def set_cuda_backend_impl(impl: CudaBackendImpl) -> None:
 
 def get_cuda_backend_impl() -> CudaBackendImpl:
   return CudaBackendImpl(_cuda_ext.get_cuda_backend_impl())
+
+
+def launch_count() -> int:
+  """Kernels launched by libffpa_b200.so since load (bench.py reports it as ``gpu_launches``)."""
+  return int(_cuda_ext.launch_count())
 
 
 _OP_NAMESPACE = "ffpa_attn"
@@ -86,12 +98,34 @@ torch.library.define(
 )
 
 
+class _Flag:
+  """Per-thread switch read by the backward ops (set by functional._FFPAAttnFunc.backward from
+  ``CUDABackend.bwd_min_workspace``): True = O(N)-memory recompute kernels, no score stash."""
+
+  def __init__(self):
+    import threading
+    self._tls = threading.local()
+
+  def get(self) -> bool:
+    return bool(getattr(self._tls, "v", False))
+
+  def set(self, v: bool) -> None:
+    self._tls.v = bool(v)
+
+
+_BWD_MIN_WORKSPACE = _Flag()
+
+
 @torch.library.impl(f"{_OP_NAMESPACE}::_bwd_cuda", "CUDA")
 def _bwd_cuda_torch_op(Q, K, V, O, softmax_lse, dO, stages, causal, softmax_scale):
   dQ = torch.empty_like(Q, memory_format=torch.contiguous_format)
   dK = torch.empty_like(K, memory_format=torch.contiguous_format)
   dV = torch.empty_like(V, memory_format=torch.contiguous_format)
-  _cuda_ext.ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale)
+  if _BWD_MIN_WORKSPACE.get():
+    _cuda_ext.ffpa_attn_backward_ex(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale,
+                                    min_workspace=True)
+  else:
+    _cuda_ext.ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale)
   return dQ, dK, dV
 
 
@@ -120,17 +154,16 @@ def _bwd_cuda_ex_torch_op(Q, K, V, O, softmax_lse, dO, attn_bias, stages, causal
   dK = torch.empty_like(K, memory_format=torch.contiguous_format)
   dV = torch.empty_like(V, memory_format=torch.contiguous_format)
   has_bias = attn_bias.numel() > 0
-  d_full = None
+  d32 = None
   if bias_grad and has_bias:
-    d_full = torch.zeros(Q.size(0), Q.size(1), Q.size(2), K.size(2), dtype=torch.float32, device=Q.device)
-  _cuda_ext.ffpa_attn_backward(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale,
-                               attn_bias=attn_bias if has_bias else None, dropout_p=dropout_p,
-                               philox_seed=philox_seed, philox_offset=philox_offset, d_bias=d_full)
-  if d_full is not None:
-    red = [i for i in range(4) if attn_bias.size(i) == 1 and d_full.size(i) != 1]
-    dbias = (d_full.sum(dim=red, keepdim=True) if red else d_full).to(attn_bias.dtype)
-  else:
-    dbias = Q.new_empty(0)
+    # bias-shaped fp32 accumulator: the dQ kernel reduces dS over the bias' broadcast dims itself (never a
+    # [B, Hq, Nq, Nkv] buffer for a [B, 1, 1, Nkv] bias); the library zero-fills it
+    d32 = torch.empty(attn_bias.shape, dtype=torch.float32, device=Q.device)
+  _cuda_ext.ffpa_attn_backward_ex(Q, K, V, O, softmax_lse, dO, dQ, dK, dV, stages, causal, softmax_scale,
+                                  attn_bias=attn_bias if has_bias else None, dropout_p=dropout_p,
+                                  philox_seed=philox_seed, philox_offset=philox_offset, d_bias=d32,
+                                  min_workspace=_BWD_MIN_WORKSPACE.get())
+  dbias = d32.to(attn_bias.dtype) if d32 is not None else Q.new_empty(0)
   return dQ, dK, dV, dbias
 
 
@@ -195,7 +228,7 @@ def _varlen_bwd_cuda_fake(Q, K, V, O, softmax_lse, dO, cu_q, cu_k, max_q, max_k,
 def _ffpa_attn_forward_cuda(Q, K, V, O, attn_bias, stages, acc, causal, softmax_scale,
                             dropout_p=0.0, philox_seed=0, philox_offset=0, fp8_smooth_k=True,
                             fp8_smooth_v=False, fp8_q_quant_method=0, fp8_k_quant_method=0,
-                            fp8_v_quant_method=0, fp8_pv_acc_type=0, fp8_qk_mm_type=0,
+                            fp8_v_quant_method=0, fp8_pv_acc_type=1, fp8_qk_mm_type=0,
                             fp8_hybrid=False, fp8_hybrid_n_early=256, fp4_hybrid=False,
                             fp4_hybrid_n_early=256):
   """Python wrapper with the reference's argument order (cuda/_ffpa_fwd.py:6-62).

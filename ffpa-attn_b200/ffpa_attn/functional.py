@@ -22,6 +22,7 @@ from dataclasses import dataclass, field
 import torch
 
 from .cuda import (
+  _BWD_MIN_WORKSPACE,
   CUDA_BWD_AVAILABLE,
   CudaBackendImpl,
   _ffpa_attn_backward_cuda,
@@ -30,8 +31,9 @@ from .cuda import (
 )
 
 _ACC_F16, _ACC_F32 = 0, 1
-_QUANT_CODE = {"per_block": 0, "per_thread": 1, "per_channel": 1}
-_PV_ACC_CODE = {"f32": 0, "f16": 1}
+# codes of the reference's op signature (/root/reference/src/ffpa_attn/functional.py:46-67)
+_QUANT_CODE = {"per_block": 0, "per_channel": 1, "per_thread": 2}
+_PV_ACC_CODE = {"f16": 0, "f32": 1}
 _QK_MM_TYPE_CODE = {"fp8": 0, "int8": 1}
 
 
@@ -49,8 +51,14 @@ class CUDABackend:
 
   All reference fields are accepted so existing call sites keep working; on B200 they select
   between two kernels only: the fp16/bf16 tcgen05 kernel (default) and the FP8 kernel
-  (``enable_fp8=True``).  ``stages``/``enable_tma``/``enable_cute``/``enable_ws`` are advisory:
-  the sm_100a kernel is always TMA-fed and warp-specialised with a static pipeline depth.
+  (``enable_fp8=True``).  ``stages``/``enable_tma``/``enable_cute``/``enable_ws`` describe properties every
+  sm_100a kernel already has (TMA-fed, warp-specialised, static pipeline depth per head dim) and change
+  nothing.  Knobs that would change numerics but select sm_120 ``mma.sync`` variants this build does not have
+  (``fp8_q/k_quant_method="per_thread"``, ``fp8_qk_mm_type="int8"``, ``fp8_pv_acc_type="f16"``) raise
+  ``NotImplementedError`` naming the knob -- they are never silently dropped.
+  ``bwd_min_workspace`` (B200 extra): True forces the O(N)-memory backward (three recompute kernels);
+  by default the backward may use an O(Nq*Nkv) score stash taken from at most half of the memory that is
+  free anyway (see csrc/ffpa_torch_binding.cpp), falling back to the O(N) plan when allocation fails.
   """
   name: str = "cuda"
   acc: str = "f32"
@@ -74,6 +82,7 @@ class CUDABackend:
   is_causal: bool = False
   forward: bool = True
   backward: bool = True  # unlike the reference (functional.py:266-268) a CUDA backward exists
+  bwd_min_workspace: bool = False
 
   def __post_init__(self) -> None:
     if self.name != "cuda":
@@ -97,6 +106,21 @@ class CUDABackend:
       raise ValueError(f"fp8_pv_acc_type must be 'f32' or 'f16', got {self.fp8_pv_acc_type!r}")
     if self.fp8_qk_mm_type not in _QK_MM_TYPE_CODE:
       raise ValueError(f"fp8_qk_mm_type must be 'fp8' or 'int8', got {self.fp8_qk_mm_type!r}")
+    if self.fp8_smooth_v and self.fp8_v_quant_method != "per_channel":
+      # reference: functional.py:300-302
+      raise ValueError("fp8_smooth_v requires fp8_v_quant_method='per_channel'")
+    if self.enable_fp8:
+      # result-changing knobs without an sm_100a implementation are refused, not ignored (the native layer
+      # refuses them too for callers that bypass this class)
+      if "per_thread" in (self.fp8_q_quant_method, self.fp8_k_quant_method):
+        raise NotImplementedError(
+          "CUDABackend: fp8_q_quant_method / fp8_k_quant_method='per_thread' is not implemented on sm_100a "
+          "(per-thread scales follow the mma.sync fragment layout); use 'per_block'")
+      if self.fp8_qk_mm_type == "int8":
+        raise NotImplementedError("CUDABackend: fp8_qk_mm_type='int8' is not implemented on sm_100a; use 'fp8'")
+      if self.fp8_pv_acc_type == "f16":
+        raise NotImplementedError(
+          "CUDABackend: fp8_pv_acc_type='f16' is not implemented on sm_100a (TMEM accumulators are fp32); use 'f32'")
 
   @property
   def acc_code(self) -> int:
@@ -324,6 +348,7 @@ class _FFPAAttnFunc(torch.autograd.Function):
     bias = ctx.attn_bias
     p_drop = meta.attn_meta.dropout_p
     stages = meta.backward_meta.stages
+    _BWD_MIN_WORKSPACE.set(bool(getattr(meta.backward_meta, "bwd_min_workspace", False)))
     if bias is None and p_drop <= 0.0:
       dq, dk, dv = _ffpa_attn_backward_cuda(
         q, k, v, O, lse, d_o.contiguous(), stages, int(meta.attn_meta.is_causal), meta.attn_meta.scale)

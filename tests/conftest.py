@@ -28,3 +28,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
   return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _fresh_tuning_env():
+  """libffpa_b200.so caches the FFPA_* tuning variables per process; tests that monkeypatch them call
+  ``_C.refresh_env()`` themselves, and this makes the restored environment visible to the next test."""
+  yield
+  mod = sys.modules.get("ffpa_attn._C")
+  if mod is not None and hasattr(mod, "refresh_env"):
+    mod.refresh_env()

@@ -273,7 +273,8 @@ def _raw_backward(q, k, v, d_o, causal, min_workspace):
   out, lse = _ffpa_attn_forward_cuda(q, k, v, None, None, 0, 1, int(causal), scale)
   dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
   n0 = ffpa_attn._C.launch_count()
-  _C.ffpa_attn_backward(q, k, v, out, lse, d_o, dq, dk, dv, 0, int(causal), scale, min_workspace=min_workspace)
+  _C.refresh_env()
+  _C.ffpa_attn_backward_ex(q, k, v, out, lse, d_o, dq, dk, dv, 0, int(causal), scale, min_workspace=min_workspace)
   torch.cuda.synchronize()
   return dq, dk, dv, ffpa_attn._C.launch_count() - n0
 
@@ -312,10 +313,15 @@ def test_backward_stash_chunked_by_memory_cap(monkeypatch):
   q, k, v, d_o = _mk(B, Hq, Hkv, N, N, D, torch.bfloat16, seed=23)
   full_q, full_k, full_v, n_full = _raw_backward(q, k, v, d_o, True, False)
   assert n_full == 4
-  ws_full = int(_C._lib.ffpa_b200_bwd_workspace_bytes(B, Hq, Hkv, N, N, D))
-  monkeypatch.setenv("FFPA_BWD_STASH_MAX_GB", "0.1")
-  ws_cap = int(_C._lib.ffpa_b200_bwd_workspace_bytes(B, Hq, Hkv, N, N, D))
-  assert ws_cap < 0.11 * 2 ** 30 + 2 ** 22 < ws_full
+  import ctypes
+
+  import capi
+  lib = capi.load()
+  sizes = capi.bwd_sizes(B, Hq, Hkv, N, N, D)
+  ws_full = int(lib.ffpa_b200_bwd_workspace_bytes_p(ctypes.byref(sizes), 1 << 40))
+  monkeypatch.setenv("FFPA_BWD_STASH_MAX_GB", "0.1")   # the binder's upper bound on the scratch it offers
+  ws_cap = int(lib.ffpa_b200_bwd_workspace_bytes_p(ctypes.byref(sizes), int(0.1 * 2 ** 30)))
+  assert ws_cap <= 0.1 * 2 ** 30 < ws_full
   cq, ck, cv, n_chunked = _raw_backward(q, k, v, d_o, True, False)
   assert n_chunked == 4 * 2 * 3   # 2 batch elements x KV-head chunks (3, 3, 2), 4 launches each
   for a, b_ in ((cq, full_q), (ck, full_k), (cv, full_v)):

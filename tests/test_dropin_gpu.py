@@ -1,0 +1,83 @@
+"""The drop-in proof: the reference's Python package, UNMODIFIED
+(pip-installed from /root/reference into the git-ignored baseline/_ref by tools/install_reference.sh), with
+this repo's compiled ``ffpa_attn._C`` dropped next to it, serves ``ffpa_attn_func(..., forward_backend="cuda")``
+on the sm_100a kernels: bf16/fp16, causal, GQA, bool / additive masks, dropout, FP8 (with
+FFPA_CUDA_ALLOW_SMALL_D=1 for D=256) incl. the causal hybrid, and composes with the reference's own SDPA and
+Triton backwards through the unchanged saved-tensor contract. Runs in a subprocess because both packages
+register ``torch.ops.ffpa_attn._fwd_cuda``."""
+import glob
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_PKG = os.path.join(ROOT, "baseline", "_ref", "ffpa_attn")
+OURS = os.path.join(ROOT, "ffpa-attn_b200", "ffpa_attn")
+
+
+@pytest.fixture(scope="module")
+def dropin(tmp_path_factory):
+  if not os.path.isdir(REF_PKG):
+    pytest.skip("baseline/_ref/ffpa_attn is absent: run tools/install_reference.sh where /root/reference exists")
+  d = tmp_path_factory.mktemp("dropin")
+  dst = os.path.join(d, "ffpa_attn")
+  shutil.copytree(REF_PKG, dst, ignore=shutil.ignore_patterns("__pycache__"))
+  # byte-identical to the installed reference: nothing of it is edited
+  for rel in ("functional.py", "cuda/__init__.py", "ffpa_attn_interface.py"):
+    assert open(os.path.join(dst, rel), "rb").read() == open(os.path.join(REF_PKG, rel), "rb").read()
+  so = glob.glob(os.path.join(OURS, "_C*.so"))
+  assert so, "ffpa_attn._C is not built"
+  shutil.copy(so[0], dst)
+  shutil.copy(os.path.join(OURS, "libffpa_b200.so"), dst)
+  env = dict(os.environ, PYTHONPATH=str(d), FFPA_REPO_ROOT=ROOT, FFPA_CUDA_ALLOW_SMALL_D="1")
+  p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_runner.py")], env=env, cwd=str(d),
+                     capture_output=True, text=True, timeout=1500)
+  lines = [l for l in p.stdout.splitlines() if l.startswith("DROPIN_JSON ")]
+  assert lines, f"runner failed rc={p.returncode}\nstdout: {p.stdout[-3000:]}\nstderr: {p.stderr[-3000:]}"
+  res = json.loads(lines[-1][len("DROPIN_JSON "):])
+  assert res["package_file"].startswith(str(d)), res["package_file"]
+  assert os.path.dirname(res["native_module"]) == dst
+  return res
+
+
+def _ok(res, name):
+  r = res[name]
+  assert "error" not in r, r.get("error")
+  return r
+
+
+def test_reference_package_sees_our_native_module(dropin):
+  assert dropin["cuda_fwd_available"] is True and dropin["import_error"] == "None"
+
+
+@pytest.mark.parametrize("name,tol", [("bf16_plain_d512", 1e-2), ("fp16_causal_gqa_d320", 1e-2), ("bool_mask_d512", 2e-2),
+                                      ("key_padding_additive_d512", 2e-2), ("dropout_d512", 4e-2)])
+def test_unmodified_reference_api_runs_on_our_kernels(dropin, name, tol):
+  r = _ok(dropin, name)
+  assert r["launches"] >= 1, "launch counter of libffpa_b200.so did not advance"
+  assert r["err"] < tol, r
+  if name == "dropout_d512":
+    assert r["rng_advanced"] == 1 * 2 * 512 * 512   # functional.py:535-540 reserves one Philox output per score
+
+
+def test_fp8_through_the_reference_api(dropin):
+  r = _ok(dropin, "fp8_d256_small_d_env")
+  assert r["err"] < 4e-2 and r["differs_from_16bit"] and r["launches"] >= 3   # /root/reference/tests/test_ffpa_fp8.py:71
+  r = _ok(dropin, "fp8_causal_hybrid_d512")
+  assert r["err"] < 1e-1 and r["early_rows_bit_equal_16bit"] and r["late_rows_differ"]
+  r = _ok(dropin, "fp8_unsupported_knob_raises")
+  assert r["raised"] == "NotImplementedError" and "int8" in r["msg"]
+
+
+def test_reference_backwards_compose_with_our_forward(dropin):
+  r = _ok(dropin, "our_forward_plus_reference_sdpa_backward_d512")
+  assert max(r["dq"], r["dk"], r["dv"]) < 5e-2, r
+  r = dropin["our_forward_plus_reference_triton_backward_d320"]
+  if "error" in r:
+    pytest.skip("the reference's Triton backward does not run on this box: " + r["error"].strip().splitlines()[-1])
+  assert max(r["dq"], r["dk"], r["dv"]) < 1e-1, r

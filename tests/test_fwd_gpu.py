@@ -293,6 +293,10 @@ def test_c5_headdim_sweep_sampled(D):
   _sampled_rows_check(q, k, v, out, [0, 100, 4097, 8191], [(0, 0), (0, 3)], False, 1e-2)
 
 
+# the 11 trailing fp8 / fp4 arguments of ffpa_attn_forward at their reference defaults (cuda/_ffpa_fwd.py:6-30)
+_FP8_DEFAULTS = (True, False, 0, 0, 0, 1, 0, False, 256, False, 256)
+
+
 def test_errors_raised_by_native_layer():
   import ffpa_attn._C as C
 
@@ -300,11 +304,19 @@ def test_errors_raised_by_native_layer():
   o = torch.empty_like(q)
   lse = torch.empty(1, 2, 64, dtype=torch.float32, device=DEV)
   with pytest.raises(RuntimeError):  # causal with Nkv < Nq  (launch.cuh:79-129 TORCH_CHECK class)
-    C.ffpa_attn_forward(q, k[:, :, :32], v[:, :, :32], q.new_empty(0), o, lse, 0, 1, 1, 0.125, 0.0, 0, 0)
+    C.ffpa_attn_forward(q, k[:, :, :32], v[:, :, :32], q.new_empty(0), o, lse, 0, 1, 1, 0.125, 0.0, 0, 0, *_FP8_DEFAULTS)
   with pytest.raises(ValueError):  # dtype
-    C.ffpa_attn_forward(q.float(), k.float(), v.float(), q.new_empty(0), o.float(), lse, 0, 1, 0, 0.125, 0.0, 0, 0)
+    C.ffpa_attn_forward(q.float(), k.float(), v.float(), q.new_empty(0), o.float(), lse, 0, 1, 0, 0.125, 0.0, 0, 0, *_FP8_DEFAULTS)
+  with pytest.raises(ValueError):  # acc = f16 does not exist on sm_100a (std::invalid_argument class, ffpa_api.cc:180-205)
+    C.ffpa_attn_forward(q, k, v, q.new_empty(0), o, lse, 0, 0, 0, 0.125, 0.0, 0, 0, *_FP8_DEFAULTS)
   with pytest.raises(RuntimeError):  # bias + causal
-    C.ffpa_attn_forward(q, k, v, torch.zeros(1, 1, 64, 64, device=DEV), o, lse, 0, 1, 1, 0.125, 0.0, 0, 0)
+    C.ffpa_attn_forward(q, k, v, torch.zeros(1, 1, 64, 64, device=DEV), o, lse, 0, 1, 1, 0.125, 0.0, 0, 0, *_FP8_DEFAULTS)
+  # zero-sized problems return without a launch (B == 0, Nq == 0) or give the empty-row convention (Nkv == 0)
+  n0 = C.launch_count()
+  C.ffpa_attn_forward(q[:0], k[:0], v[:0], q.new_empty(0), o[:0], q.new_empty(0), 0, 1, 0, 0.125, 0.0, 0, 0, *_FP8_DEFAULTS)
+  C.ffpa_attn_forward(q, k[:, :, :0], v[:, :, :0], q.new_empty(0), o, lse, 0, 1, 0, 0.125, 0.0, 0, 0, *_FP8_DEFAULTS)
+  assert C.launch_count() == n0
+  assert torch.all(o == 0) and torch.all(lse == float("-inf"))
 
 
 def test_torch_compile_sees_the_op():  # tests/test_ffpa_compile.py:53-71
@@ -366,6 +378,7 @@ def test_replay_path_matches_two_pass_path_and_oracle(D, causal, shape, monkeypa
   o_replay, lse_replay = _lse(q, k, v, causal)
   n_replay = ffpa_attn._C.launch_count() - n0
   monkeypatch.setenv("FFPA_FWD_REPLAY", "0")
+  ffpa_attn._C.refresh_env()   # the library caches its tuning variables per process
   n0 = ffpa_attn._C.launch_count()
   o_two, lse_two = _lse(q, k, v, causal)
   n_two = ffpa_attn._C.launch_count() - n0

@@ -1,6 +1,7 @@
 """CPU tests for the boundary: the C-ABI library loads and exports every symbol declared in
-include/ffpa_b200.h, the ctypes structs match the C layout, and the host-side mirror of the
-reference API validates inputs with the reference's error classes. No kernel is launched."""
+include/ffpa_b200.h, the ctypes structs (tests/capi.py) match the C layout, the PyTorch extension
+``ffpa_attn._C`` exports the reference module's pybind surface (ffpa_api.cc:265-306), and the host-side mirror
+of the reference API validates inputs with the reference's error classes. No kernel is launched."""
 import ctypes
 import os
 import re
@@ -10,6 +11,9 @@ import tempfile
 
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import capi  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "ffpa_b200.h")
@@ -23,7 +27,7 @@ def lib():
     import __graft_entry__ as ge
 
     ge.build()
-  return ctypes.CDLL(LIB)
+  return capi.load()
 
 
 def _declared_symbols():
@@ -34,8 +38,8 @@ def _declared_symbols():
 def test_header_declares_expected_entry_points():
   syms = _declared_symbols()
   for s in ("ffpa_b200_fwd", "ffpa_b200_bwd", "ffpa_b200_set_backend_impl", "ffpa_b200_get_backend_impl",
-            "ffpa_b200_last_error", "ffpa_b200_launch_count", "ffpa_b200_bwd_workspace_bytes",
-            "ffpa_b200_fwd_workspace_bytes"):
+            "ffpa_b200_last_error", "ffpa_b200_launch_count", "ffpa_b200_bwd_workspace_bytes_p",
+            "ffpa_b200_bwd_workspace_bytes_min_p", "ffpa_b200_fwd_workspace_bytes_p"):
     assert s in syms
 
 
@@ -46,12 +50,12 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_flags(lib):
   lib.ffpa_b200_abi_version.restype = ctypes.c_int32
-  assert lib.ffpa_b200_abi_version() == 2
+  assert lib.ffpa_b200_abi_version() == 3
   assert lib.ffpa_b200_fwd_available() == 1
 
 
 def test_ctypes_struct_layout_matches_c():
-  import ffpa_attn._C as C
+  C = capi
 
   prog = r"""
 #include <stdio.h>
@@ -63,6 +67,10 @@ int main(void) {
          offsetof(ffpa_fwd_params, philox_seed), offsetof(ffpa_fwd_params, philox_offset),
          offsetof(ffpa_fwd_params, workspace_bytes), offsetof(ffpa_fwd_params, cu_seqlens_q),
          offsetof(ffpa_fwd_params, total_k));
+  printf("%zu %zu %zu %zu %zu ", offsetof(ffpa_fwd_params, impl), offsetof(ffpa_fwd_params, fp8_smooth_k),
+         offsetof(ffpa_fwd_params, fp8_qk_mm_type), offsetof(ffpa_fwd_params, fp8_hybrid_n_early),
+         offsetof(ffpa_fwd_params, lse_bh_stride));
+  printf("%zu ", offsetof(ffpa_bwd_params, d_bias_stride));
   printf("%zu %zu %zu %zu %zu %zu %zu %zu ", sizeof(ffpa_bwd_params), offsetof(ffpa_bwd_params, batch),
          offsetof(ffpa_bwd_params, softmax_scale), offsetof(ffpa_bwd_params, workspace),
          offsetof(ffpa_bwd_params, bias_kind), offsetof(ffpa_bwd_params, d_bias),
@@ -77,10 +85,12 @@ int main(void) {
     exe = os.path.join(d, "t")
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
     out = subprocess.check_output([exe]).decode().split()
-  F, B = C._FwdParams, C._BwdParams
+  F, B = C.FwdParams, C.BwdParams
   want = [ctypes.sizeof(F), F.bias_stride.offset, F.batch.offset, F.softmax_scale.offset,
           F.philox_seed.offset, F.philox_offset.offset, F.workspace_bytes.offset,
           F.cu_seqlens_q.offset, F.total_k.offset,
+          F.impl.offset, F.fp8_smooth_k.offset, F.fp8_qk_mm_type.offset, F.fp8_hybrid_n_early.offset,
+          F.lse_bh_stride.offset, B.d_bias_stride.offset,
           ctypes.sizeof(B), B.batch.offset, B.softmax_scale.offset, B.workspace.offset,
           B.bias_kind.offset, B.d_bias.offset, B.cu_seqlens_k.offset, B.total_q.offset, B.d_lse.offset]
   assert [int(x) for x in out] == want
@@ -99,13 +109,50 @@ def test_backend_hint_roundtrip(lib):
 def test_c_abi_rejects_bad_arguments_without_a_gpu(lib):
   """Argument validation happens before any CUDA work except the device probe; on a box with no
   GPU every call must fail loudly (no silent CPU path)."""
+  p = capi.FwdParams()
+  rc = lib.ffpa_b200_fwd(ctypes.byref(p), None)
+  assert rc < 0
+  assert len(lib.ffpa_b200_last_error()) > 0
+  assert lib.ffpa_b200_fwd(None, None) == -1
+  assert lib.ffpa_b200_bwd(None, None) == -1
+
+
+def test_torch_extension_exports_the_reference_pybind_surface():
+  """ffpa_attn._C is a compiled PyTorch extension (not a Python shim) with the names, attributes and argument
+  counts of /root/reference/csrc/cuffpa/ffpa_api.cc:265-306 (forward: 24 positional arguments, :86-96;
+  backward: 12, :242-246)."""
   import ffpa_attn._C as C
 
-  p = C._FwdParams()
-  rc = C._lib.ffpa_b200_fwd(ctypes.byref(p), None)
-  assert rc < 0
-  assert len(C._lib.ffpa_b200_last_error()) > 0
-  assert C._lib.ffpa_b200_fwd(None, None) == -1
+  assert C.__file__.endswith(".so")
+  for name in ("ffpa_attn_forward", "ffpa_attn_backward", "set_cuda_backend_impl", "get_cuda_backend_impl"):
+    assert callable(getattr(C, name))
+  for attr, want in (("CUDA_FWD_AVAILABLE", True), ("CUDA_AVAILABLE", True), ("F16_ACC_AVAILABLE", False),
+                     ("CUDA_TMA_AVAILABLE", True), ("CUDA_CUTE_TMA_AVAILABLE", False), ("CUDA_BWD_AVAILABLE", True)):
+    assert getattr(C, attr) is want
+  assert C.ABI_VERSION == 3
+  doc = C.ffpa_attn_forward.__doc__.split("->")[0]
+  assert doc.count("arg") == 24, doc
+  assert C.ffpa_attn_backward.__doc__.split("->")[0].count("arg") == 12
+  t = torch.zeros(1, 1, 8, 64, dtype=torch.bfloat16)
+  e = torch.empty(0)
+  with pytest.raises(RuntimeError, match="CUDA tensors"):   # CPU tensors: no fallback path
+    C.ffpa_attn_forward(t, t, t, e, t.clone(), e, 0, 1, 0, 0.125, 0.0, 0, 0, True, False, 0, 0, 0, 1, 0, False, 256, False, 256)
+
+
+def test_backend_hint_is_thread_local(lib):
+  """The reference keeps one process-global atomic (backend.h:16-25): two threads using different backends
+  race. Here the hint set by a thread is visible to that thread only."""
+  import threading
+
+  import ffpa_attn._C as C
+
+  C.set_cuda_backend_impl(5)
+  seen = []
+  t = threading.Thread(target=lambda: seen.append(C.get_cuda_backend_impl()))
+  t.start()
+  t.join()
+  assert seen == [0] and C.get_cuda_backend_impl() == 5
+  C.set_cuda_backend_impl(0)
 
 
 # ---- host-side API semantics (reference: tests/test_ffpa_fwd.py:162-177, 1146-1152, 1199-1215) ----
@@ -268,43 +315,84 @@ def test_varlen_host_validation_and_no_cpu_fallback():
     ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16)
 
 
-def test_backward_workspace_plan(lib, monkeypatch):
-  """ffpa_b200_bwd_workspace_bytes = required scratch + the two 16-bit score buffers of the stash path for head
-  dims 384..1024, bounded by FFPA_BWD_STASH_MAX_GB (KV-head chunks beyond it); _min = required scratch only."""
-  f, m = lib.ffpa_b200_bwd_workspace_bytes, lib.ffpa_b200_bwd_workspace_bytes_min
-  for fn in (f, m):
-    fn.argtypes = [ctypes.c_int32] * 6
-    fn.restype = ctypes.c_uint64
-  monkeypatch.delenv("FFPA_BWD_STASH_MAX_GB", raising=False)
-  monkeypatch.delenv("FFPA_BWD_STASH", raising=False)
+def test_backward_workspace_plan(lib):
+  """_min_p = required O(N) scratch; _p(params, cap) = recommended size under `cap`: for head dims 384..1024 it
+  adds the two 16-bit score buffers of the stash path, cut into (batch, KV-head) chunks when they do not fit,
+  and degrades to the minimum when not even a machine-filling chunk fits. cap == 0 asks for the minimum."""
+  f, m = lib.ffpa_b200_bwd_workspace_bytes_p, lib.ffpa_b200_bwd_workspace_bytes_min_p
+  big = 1 << 40
+
+  def F(*a, cap=big):
+    return f(ctypes.byref(capi.bwd_sizes(*a)), cap)
+
+  def M(*a):
+    return m(ctypes.byref(capi.bwd_sizes(*a)))
+
   B, H, N, D = 1, 32, 8192, 512
   stash = 2 * B * H * N * N * 2
-  assert f(B, H, H, N, N, D) == m(B, H, H, N, N, D) + stash
-  assert f(B, H, H, N, N, 256) == m(B, H, H, N, N, 256)            # small heads: recompute kernels
-  assert f(B, H, H, N, N, 1024) == m(B, H, H, N, N, 1024) + stash   # large heads: stash on the first slab pass
-  assert f(1, 4, 2, 130, 257, 512) == m(1, 4, 2, 130, 257, 512) + 2 * 4 * 256 * 512 * 2   # padded to 128 x 256
-  # 4 batch elements would need 34 GB: chunked per batch element under the default 20 GB cap
-  assert f(4, H, H, N, N, D) <= 20 * 2 ** 30 + m(4, H, H, N, N, D)
-  assert f(4, H, H, N, N, D) >= stash
-  monkeypatch.setenv("FFPA_BWD_STASH", "0")
-  assert f(B, H, H, N, N, D) == m(B, H, H, N, N, D)
+  assert F(B, H, H, N, N, D) == M(B, H, H, N, N, D) + stash
+  assert F(B, H, H, N, N, 256) == M(B, H, H, N, N, 256)            # small heads: recompute kernels
+  assert F(B, H, H, N, N, 1024) == M(B, H, H, N, N, 1024) + stash   # large heads: stash on the first slab pass
+  assert F(1, 4, 2, 130, 257, 512) == M(1, 4, 2, 130, 257, 512) + 2 * 4 * 256 * 512 * 2   # padded to 128 x 256
+  assert F(B, H, H, N, N, D, cap=0) == M(B, H, H, N, N, D)
+  # 4 batch elements need 34 GB: under a 20 GB cap the plan is chunked (one batch element at a time)
+  cap = 20 << 30
+  got = F(4, H, H, N, N, D, cap=cap)
+  assert stash <= got <= cap
+  # a cap of 3 GB still fits a machine-filling chunk of KV heads; 100 MB does not -> minimum
+  got = F(B, H, H, N, N, D, cap=3 << 30)
+  assert M(B, H, H, N, N, D) < got <= 3 << 30
+  assert F(B, H, H, N, N, D, cap=100 << 20) == M(B, H, H, N, N, D)
+  # the plan is monotone in the cap
+  sizes = [F(2, 16, 4, 4096, 4096, 512, cap=c << 30) for c in (0, 1, 2, 4, 8, 64)]
+  assert sizes == sorted(sizes)
 
 
 def test_forward_workspace_plan(lib, monkeypatch):
-  """Forward scratch: KV-split partials for decode-like shapes, the replay stash for head dims > 768, FP8 copies."""
-  f = lib.ffpa_b200_fwd_workspace_bytes
-  f.argtypes = [ctypes.c_int32] * 7
-  f.restype = ctypes.c_uint64
-  monkeypatch.delenv("FFPA_FWD_REPLAY", raising=False)
-  monkeypatch.delenv("FFPA_FWD_REPLAY_MAX_GB", raising=False)
-  assert f(1, 32, 32, 8192, 8192, 512, 0) == 0
-  assert f(1, 32, 32, 8192, 8192, 768, 0) == 0
-  need = f(1, 32, 32, 8192, 8192, 1024, 0)
-  assert 32 * 8192 * 8192 * 2 <= need <= 32 * 8192 * 8192 * 2 * 1.02   # P tiles + factors + 1/rowsum
-  assert f(1, 32, 32, 1, 8192, 512, 0) > 0     # decode: KV-split partials
-  assert f(1, 32, 32, 8192, 8192, 256, 1) > 3 * 32 * 8192 * 256   # FP8: e4m3 copies of Q, K, V + scales
-  monkeypatch.setenv("FFPA_FWD_REPLAY", "0")
-  assert f(1, 32, 32, 8192, 8192, 1024, 0) == 0
+  """Forward scratch: KV-split partials for decode-like shapes, the replay stash for head dims > 768, FP8 copies,
+  and for FP8 hybrid the larger of its two stages."""
+  f = lib.ffpa_b200_fwd_workspace_bytes_p
+
+  def F(*a, **kw):
+    return f(ctypes.byref(capi.fwd_sizes(*a, **kw)))
+
+  assert F(1, 32, 32, 8192, 8192, 512) == 0
+  assert F(1, 32, 32, 8192, 8192, 768) == 0
+  need = F(1, 32, 32, 8192, 8192, 1024)
+  if os.environ.get("FFPA_FWD_REPLAY", "1") != "0":
+    assert 32 * 8192 * 8192 * 2 <= need <= 32 * 8192 * 8192 * 2 * 1.02   # P tiles + factors + 1/rowsum
+  assert F(1, 32, 32, 1, 8192, 512) > 0     # decode: KV-split partials
+  fp8 = F(1, 32, 32, 8192, 8192, 256, impl=5)
+  assert fp8 > 3 * 32 * 8192 * 256           # FP8: e4m3 copies of Q, K, V + scales
+  hyb = F(1, 32, 32, 8192, 8192, 256, impl=5, causal=1, fp8_hybrid=1, fp8_hybrid_n_early=256)
+  assert 0 < hyb <= fp8                      # stage 2 quantises 256 fewer query rows
+  assert F(1, 32, 32, 8192, 8192, 256, impl=5, fp8_q_quant_method=2) == 0   # refused knob: nothing to plan
+
+
+def test_unsupported_fp8_knobs_are_refused_by_name(lib):
+  """per_thread Q/K scales, int8 QK and the f16 PV accumulator select sm_120 variants: the native layer refuses
+  them (FFPA_ERR_UNSUPPORTED = -2, knob named) instead of ignoring them; so does CUDABackend."""
+  from ffpa_attn import CUDABackend
+
+  base = dict(q=1, k=1, v=1, o=1, dtype=1, impl=5)
+  for kw, word in ((dict(fp8_q_quant_method=2, fp8_k_quant_method=2), b"per_thread"), (dict(fp8_qk_mm_type=1), b"int8"),
+                   (dict(fp8_pv_acc_type=0), b"f16")):
+    p = capi.fwd_sizes(1, 2, 2, 256, 256, 128, **base)
+    for i in range(4):
+      p.q_stride[i] = p.k_stride[i] = p.v_stride[i] = p.o_stride[i] = (1 if i == 3 else 128)
+    for k, v in kw.items():
+      setattr(p, k, v)
+    rc = lib.ffpa_b200_fwd(ctypes.byref(p), None)
+    # without a GPU the device probe fails first (-4); with one the knob is refused (-2)
+    assert rc in (-2, -4)
+    if rc == -2:
+      assert word in lib.ffpa_b200_last_error()
+  for kw in (dict(fp8_q_quant_method="per_thread"), dict(fp8_qk_mm_type="int8"), dict(fp8_pv_acc_type="f16")):
+    with pytest.raises(NotImplementedError):
+      CUDABackend(enable_fp8=True, **kw)
+    CUDABackend(**kw)   # harmless while FP8 is off, as in the reference
+  with pytest.raises(ValueError, match="per_channel"):
+    CUDABackend(enable_fp8=True, fp8_smooth_v=True)
 
 
 def test_fp8_hybrid_auto_resolution():

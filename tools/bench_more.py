@@ -89,8 +89,8 @@ def main():
 
         o2, lse2 = _ffpa_attn_forward_cuda(q, k, v, None, None, 0, 1, int(causal), D ** -0.5)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        ms_r = timeit(lambda: _C.ffpa_attn_backward(q, k, v, o2, lse2, d_o, dq, dk, dv, 0, int(causal), D ** -0.5,
-                                                    min_workspace=True), 5)
+        ms_r = timeit(lambda: _C.ffpa_attn_backward_ex(q, k, v, o2, lse2, d_o, dq, dk, dv, 0, int(causal), D ** -0.5,
+                                                       min_workspace=True), 5)
         ms_s = timeit(lambda: _C.ffpa_attn_backward(q, k, v, o2, lse2, d_o, dq, dk, dv, 0, int(causal), D ** -0.5), 5)
         rec.update({"bwd_recompute_ms": ms_r, "bwd_recompute_tflops": 2.5 * f / ms_r * 1e-9,
                     "bwd_stash_ms": ms_s, "bwd_stash_tflops": 2.5 * f / ms_s * 1e-9})
