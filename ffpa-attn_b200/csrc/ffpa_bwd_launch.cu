@@ -204,6 +204,7 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream) {
   for (int i = 0; i < 4; ++i) kp.bias_stride[i] = a.bias_stride[i];
   kp.dropout_p = a.dropout_p; kp.philox_seed = a.philox_seed; kp.philox_offset = a.philox_offset;
   kp.dbias = a.d_bias;
+  kp.zero_single = a.d_lse == nullptr;
   for (int i = 0; i < 4; ++i) kp.dbias_stride[i] = a.d_bias_stride[i];
   if (a.d_bias) {
     // the dQ kernel accumulates into the bias-shaped buffer (atomics wherever a dim is reduced): start from zero

@@ -527,6 +527,13 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
         } else {
           if (p.causal) lim_lo = grow - off;
         }
+        // A query that sees at most ONE key has an analytically zero dS row (dP == delta when P == 1): write the
+        // exact zero instead of the ~1 ulp residue of two differently ordered fp32 reductions (the reference's
+        // sm_100 kernels make the same promise, /root/reference/tests/test_ffpa_cute_sm100.py:1000-1050).
+        // single_hi: queries <= single_hi are such rows (causal: q + off <= 0; otherwise all when Nkv == 1).
+        // (not when a gradient flows in through the LSE output: then dS = P * dLSE on such a row)
+        const int single_hi = !p.zero_single ? -0x7fffffff : p.causal ? -off : (seq_kv <= 1 ? 0x7fffffff : -1);
+        const bool any_single = (KIND == kKindDQ) ? (grow <= single_hi) : (col0 <= single_hi);
         uint32_t pk[16];
         uint32_t pp[16];  // stash path: packed P_drop, stored to global after the tile has been handed to the MMA
         const bool stash = (KIND == kKindDQ) && p.stash_ds != nullptr;   // launch-wide: T single-buffered
@@ -579,7 +586,8 @@ ffpa_bwd_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constan
             float pe = exp2f(xs);
             if (col < lim_lo || col > lim_hi) pe = 0.f;
             if (HAS_DP) {
-              const float ds = pe * (__uint_as_float(dr[jj]) * mult - dl);
+              float ds = pe * (__uint_as_float(dr[jj]) * mult - dl);
+              if (any_single && qi <= single_hi) ds = 0.f;
               e[u] = ds;
               if (KIND == kKindDQ) pv[u] = pe * mult;   // P_drop (what dV consumes), only used by the stash path
               if constexpr (GENERAL && KIND == kKindDQ) dsv[jj] = ds;

@@ -590,8 +590,10 @@ __global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const Q
   for (int i = 1; i < 32; ++i) amax = fmaxf(amax, red[i]);
   // per-channel V: every channel has its own scale (applied in the attention epilogue), block scale = 1
   const float* cam = (which == 2 && a.vamax != nullptr) ? a.vamax + ((int64_t)b * H + h) * D : nullptr;
-  const float scale = cam != nullptr ? 1.f : fmaxf(amax, 1e-12f) / 448.f;
-  const float inv = 1.f / scale;
+  // IEEE division (not the --use_fast_math reciprocal): s = amax / 448 and 1 / s are what the reference's quantiser
+  // computes (/root/reference/csrc/cuffpa/cute/fp8/quantize_fp8.cuh:140-144), so the e4m3 tiles match it bit for bit
+  const float scale = cam != nullptr ? 1.f : __fdiv_rn(fmaxf(amax, 1e-12f), 448.f);
+  const float inv = __fdiv_rn(1.f, scale);
   if (threadIdx.x == 0) {
     a.scale[which][((int64_t)b * H + h) * T + tile] = scale;
     if (which == 2) atomicMax(reinterpret_cast<unsigned int*>(a.vref + (int64_t)b * H + h), __float_as_uint(scale));

@@ -93,6 +93,7 @@ struct BwdKernelParams {
   int nk_pad;
   float* out32;   // non-null: accumulate into fp32 [B, H, out_rows, D] instead of storing `out`
   int out_rows;
+  int zero_single;  // 1: rows that see at most one key get the analytic dS = 0 (only valid without a dLSE input)
 };
 // GEMM-only dK / dV kernel over stashed score tiles (256 keys per 2-CTA cluster)
 struct BwdGemmParams {

@@ -120,3 +120,31 @@ def _side_streams(dev: torch.device):
   if key not in _STREAMS:
     _STREAMS[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
   return _STREAMS[key]
+
+
+def bind_to_gpu_numa_node(device: torch.device | str | int | None = None) -> dict | None:
+  """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that host buffers pinned
+  afterwards (first touch) are local to the GPU's PCIe root: with one process per GPU all landing on whatever
+  node the launcher left them on, every host->device copy crosses the socket interconnect and the copies of
+  different ranks contend for it. Reads only sysfs; returns {"node", "cpus", "pci"} or None when the topology
+  is not exposed (then nothing is changed)."""
+  import os
+
+  try:
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    props = torch.cuda.get_device_properties(dev)
+    bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+    node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+    if node < 0:
+      return None
+    cpus = set()
+    for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+      lo, _, hi = part.partition("-")
+      cpus.update(range(int(lo), int(hi or lo) + 1))
+    allowed = os.sched_getaffinity(0) & cpus
+    if not allowed:
+      return None
+    os.sched_setaffinity(0, allowed)
+    return {"node": node, "cpus": len(allowed), "pci": bdf}
+  except Exception:  # noqa: BLE001  (no sysfs / no attribute: leave the affinity alone)
+    return None

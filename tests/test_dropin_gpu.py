@@ -69,7 +69,9 @@ def test_fp8_through_the_reference_api(dropin):
   r = _ok(dropin, "fp8_d256_small_d_env")
   assert r["err"] < 4e-2 and r["differs_from_16bit"] and r["launches"] >= 3   # /root/reference/tests/test_ffpa_fp8.py:71
   r = _ok(dropin, "fp8_causal_hybrid_d512")
-  assert r["err"] < 1e-1 and r["early_rows_bit_equal_16bit"] and r["late_rows_differ"]
+  # early rows come from the 16-bit kernel (same kernel on a row view: agreement to rounding, 16-bit accuracy)
+  assert r["err"] < 1e-1 and r["late_rows_differ"], r
+  assert r["early_rows_max_diff_vs_16bit"] < 2e-3 and r["early_err"] < 1e-2, r
   r = _ok(dropin, "fp8_unsupported_knob_raises")
   assert r["raised"] == "NotImplementedError" and "int8" in r["msg"]
 
@@ -81,3 +83,26 @@ def test_reference_backwards_compose_with_our_forward(dropin):
   if "error" in r:
     pytest.skip("the reference's Triton backward does not run on this box: " + r["error"].strip().splitlines()[-1])
   assert max(r["dq"], r["dk"], r["dv"]) < 1e-1, r
+
+
+# ---- parity against the reference's own GPU backends (same process, identical inputs) --------------------------
+_REF_GPU_CASES = ["vs_triton_d320_fwd_bwd", "vs_triton_d320_causal_gqa_fwd_bwd", "vs_triton_d320_mask", "vs_triton_d320_dropout",
+                  "vs_triton_d512_fwd", "vs_cutedsl_d320_fwd_bwd", "vs_cutedsl_d768_fwd", "vs_cutedsl_d512_sm100_fwd_bwd"]
+
+
+@pytest.mark.parametrize("name", _REF_GPU_CASES)
+def test_matches_reference_gpu_backend(dropin, name):
+  """north_star: "Outputs must match the reference's own ffpa_attn_func". Triton (every D, mask, dropout, bwd:
+  /root/reference/src/ffpa_attn/triton/__init__.py:269-505) and CuTe-DSL (cute/__init__.py:246-281) run from the
+  unmodified package; ours runs through forward_backend="cuda" in the same process. A reference backend that does
+  not run on this box (cutlass-dsl 4.5 vs the pinned 4.6, Triton TMEM limits at D >= 512) is a SKIP that quotes
+  its error, never a silent pass."""
+  r = dropin[name]
+  if "error" in r:
+    pytest.skip(f"reference backend failed on this box: {r['error'].strip().splitlines()[-1][:300]}")
+  assert r["launches"] >= 1
+  assert r["o_err"] < (4e-2 if "dropout" in name else 2e-2), r      # two bf16/fp16 kernels against each other
+  assert r["o_cos"] > 0.9999, r
+  if "dq_rel" in r:
+    for n in ("dq", "dk", "dv"):
+      assert r[n + "_cos"] > 0.999 and r[n + "_rel"] < 5e-2, (n, r)

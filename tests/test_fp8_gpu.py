@@ -97,10 +97,11 @@ def test_fp8_smooth_v_removes_channel_mean_error():
   errs = {}
   for sv in (False, True):
     n0 = ffpa_attn._C.launch_count()
-    be = ffpa_attn.CUDABackend(enable_fp8=True, fp8_smooth_v=sv, fp8_hybrid=False)
+    # the reference requires per-channel V scales with smooth-V (functional.py:300-302); so does CUDABackend
+    be = ffpa_attn.CUDABackend(enable_fp8=True, fp8_smooth_v=sv, fp8_v_quant_method="per_channel", fp8_hybrid=False)
     out = ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=be, is_causal=True, enable_gqa=True)
     torch.cuda.synchronize()
-    assert ffpa_attn._C.launch_count() - n0 == 4 + (1 if sv else 0)
+    assert ffpa_attn._C.launch_count() - n0 == 5 + (1 if sv else 0)
     errs[sv] = float(np.abs(out.float().cpu().numpy() - ref).max())
   assert errs[True] < 4e-2, errs
   assert errs[True] < 0.5 * errs[False], errs
@@ -143,7 +144,7 @@ def test_fp8_lse_and_large_amplitude():
   ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.CUTE_TMA_FP8)
   try:
     o, lse = torch.ops.ffpa_attn._fwd_cuda(q, k, v, q.new_empty(0), 0, 1, 0, 256 ** -0.5, 0.0, 0, 0, True, False,
-                                           0, 0, 0, 0, 0, False, 256, False, 256)
+                                           0, 0, 0, 1, 0, False, 256, False, 256)
     torch.cuda.synchronize()
   finally:
     ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.AUTO)
@@ -167,7 +168,7 @@ def test_fp8_lse_small_amplitude():
   ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.CUTE_TMA_FP8)
   try:
     _, lse = torch.ops.ffpa_attn._fwd_cuda(q, k, v, q.new_empty(0), 0, 1, 0, 256 ** -0.5, 0.0, 0, 0, True, False,
-                                           0, 0, 0, 0, 0, False, 256, False, 256)
+                                           0, 0, 0, 1, 0, False, 256, False, 256)
     torch.cuda.synchronize()
   finally:
     ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.AUTO)
@@ -195,7 +196,7 @@ def test_fp8_smooth_k_handles_large_key_mean_and_corrects_lse():
   ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.CUTE_TMA_FP8)
   try:
     _, lse = torch.ops.ffpa_attn._fwd_cuda(q, k, v, q.new_empty(0), 0, 1, 0, D ** -0.5, 0.0, 0, 0, True, False,
-                                           0, 0, 0, 0, 0, False, 256, False, 256)
+                                           0, 0, 0, 1, 0, False, 256, False, 256)
     torch.cuda.synchronize()
   finally:
     ffpa_attn.set_cuda_backend_impl(fc.CudaBackendImpl.AUTO)
@@ -226,3 +227,77 @@ def test_fp8_rejects_unsupported_combinations():
   with pytest.raises(NotImplementedError):
     ffpa_attn.ffpa_attn_func(q, k, v, attn_mask=torch.ones(128, 128, dtype=torch.bool, device=DEV),
                              forward_backend=ffpa_attn.CUDABackend(enable_fp8=True))
+
+
+# ---- against the reference's QUANTISED numerics (oracle/fp8_oracle.py) ------------------------------------------
+def _fp8_layout(B, Hq, Hkv, Nq, Nkv, D):
+  """byte offsets of the FP8 scratch (csrc/ffpa_fwd_fp8.cu: fp8_layout): q8 | k8 | v8 | qs | ks | vs | ..."""
+  al = lambda x: (x + 255) // 256 * 256  # noqa: E731
+  dpad, tq, tk = (D + 15) // 16 * 16, (Nq + 127) // 128, (Nkv + 127) // 128
+  o, off = 0, {}
+  for name, n in (("q8", B * Hq * Nq * dpad), ("k8", B * Hkv * Nkv * dpad), ("v8", B * Hkv * Nkv * dpad),
+                  ("qs", B * Hq * tq * 4), ("ks", B * Hkv * tk * 4), ("vs", B * Hkv * tk * 4)):
+    off[name] = o
+    o = al(o + n)
+  return off, dpad, tq, tk
+
+
+@pytest.mark.parametrize("smooth_k", [False, True])
+def test_fp8_quantised_tiles_and_output_match_the_quantised_oracle(smooth_k):
+  """Calls the C ABI directly (ctypes) so the scratch can be read back: the e4m3 tiles and per-block scales the
+  pre-pass wrote are compared with the restatement of the reference's quantiser
+  (/root/reference/csrc/cuffpa/cute/fp8/quantize_fp8.cuh:67-168, smooth_k.cuh:61-137) -- byte for byte up to the
+  rounding of x * (1 / s) under --use_fast_math (a one-code difference on a vanishing fraction of elements) -- and
+  the attention output with the quantised oracle's (fp8_pscale.cuh:11-76 scheme), which must be CLOSER than exact
+  attention is: the kernel reproduces the reference's quantisation error, not just its magnitude."""
+  import ctypes
+
+  import capi
+  from oracle import fp8_oracle as f8
+
+  lib = capi.load()
+  B, Hq, Hkv, Nq, Nkv, D = 1, 4, 2, 384, 640, 256
+  q, k, v = _mk(B, Hq, Hkv, Nq, Nkv, D, torch.bfloat16, seed=11)
+  if smooth_k:
+    k = (k.float() + 0.75).to(torch.bfloat16)
+  o = torch.empty_like(q)
+  lse = torch.empty(B, Hq, Nq, dtype=torch.float32, device=DEV)
+  p = capi.fwd_sizes(B, Hq, Hkv, Nq, Nkv, D, impl=5, dtype=1, fp8_smooth_k=int(smooth_k), softmax_scale=D ** -0.5)
+  p.q, p.k, p.v, p.o, p.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr()
+  for name, t in (("q_stride", q), ("k_stride", k), ("v_stride", v), ("o_stride", o)):
+    setattr(p, name, (ctypes.c_int64 * 4)(*t.stride()))
+  need = lib.ffpa_b200_fwd_workspace_bytes_p(ctypes.byref(p))
+  ws = torch.zeros(need, dtype=torch.uint8, device=DEV)
+  p.workspace, p.workspace_bytes = ws.data_ptr(), need
+  rc = lib.ffpa_b200_fwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+  assert rc == 0, lib.ffpa_b200_last_error()
+  torch.cuda.synchronize()
+
+  # the kernel subtracts the fp32 mean; ask the oracle for the same (reference: mean rounded to the input dtype)
+  ref_o, ref_lse, aux = f8.fp8_attention_fwd(q.cpu(), k.cpu(), v.cpu(), smooth_k=smooth_k, mean_in_input_dtype=False)
+  off, dpad, tq, tk = _fp8_layout(B, Hq, Hkv, Nq, Nkv, D)
+  w = ws.cpu().numpy()
+  for name, H, N, T, sname in (("q8", Hq, Nq, tq, "qs"), ("k8", Hkv, Nkv, tk, "ks"), ("v8", Hkv, Nkv, tk, "vs")):
+    got = w[off[name]:off[name] + B * H * N * dpad].reshape(B, H, N, dpad)[..., :D]
+    sc = w[off[sname]:off[sname] + B * H * T * 4].view(np.float32).reshape(B, H, T)
+    want = f8.e4m3_bits(aux[name])   # aux holds the rounded VALUES; re-encode them
+    same = got == want
+    if name == "k8" and smooth_k:
+      # the sequence mean is an fp32 sum whose order differs (atomics here, a tree in torch): a last-bit difference in
+      # the mean moves a vanishing fraction of elements to the neighbouring e4m3 code
+      assert np.allclose(sc, aux[sname], rtol=1e-5, atol=0), name
+      assert same.mean() > 0.995, (name, same.mean())
+      d = np.abs(got.astype(np.int16)[~same] - want.astype(np.int16)[~same])
+      assert d.size == 0 or d.max() <= 1, (name, "mismatches must be adjacent e4m3 codes")
+    else:
+      assert np.array_equal(sc, aux[sname]), name          # s = amax / 448, IEEE division: bit-exact
+      assert same.all(), (name, same.mean())               # e4m3_rn_satfinite(x * (1 / s)): bit-exact
+  exact, exact_lse = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu())
+  got_o = o.float().cpu().numpy()
+  e_q = np.abs(got_o - ref_o).max()
+  e_x = np.abs(got_o - exact).max()
+  assert e_x < 4e-2 and e_q < 2.5e-2, (e_q, e_x)
+  # same quantised operands => the error against exact attention is (mostly) common to kernel and oracle
+  corr = np.corrcoef((got_o - exact).ravel(), (ref_o - exact).ravel())[0, 1]
+  assert corr > 0.5, corr
+  assert np.abs(lse.cpu().numpy() - exact_lse).max() < 5e-2

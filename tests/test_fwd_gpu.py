@@ -49,7 +49,7 @@ def _lse(q, k, v, causal=False, bias=None, scale=None):
     bias = q.new_empty(0)
   scale = scale if scale is not None else q.size(-1) ** -0.5
   o, lse = torch.ops.ffpa_attn._fwd_cuda(q, k, v, bias, 0, 1, int(causal), scale, 0.0, 0, 0, True, False,
-                                         0, 0, 0, 0, 0, False, 256, False, 256)
+                                         0, 0, 0, 1, 0, False, 256, False, 256)
   torch.cuda.synchronize()
   return o, lse
 
@@ -179,7 +179,7 @@ def test_fully_masked_rows_give_zero_and_neg_inf_lse():  # tests/test_ffpa_cute_
   ref, lref = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), bias=bias.double().numpy())
   _check(o, ref, 2e-2)
   fin = np.isfinite(lref)
-  assert np.abs(lse.cpu().numpy()[fin] - lref[fin]).max() < 2e-3
+  assert np.abs(lse.cpu().numpy()[fin] - lref[fin]).max() < 2e-4
 
 
 @pytest.mark.parametrize("causal", [False, True])
@@ -188,7 +188,7 @@ def test_lse_matches_oracle(causal):  # LSE abs err, tests/test_ffpa_cute_sm100.
   _, lse = _lse(q, k, v, causal=causal)
   _, lref = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), causal=causal)
   assert lse.shape == (2, 2, 300) and lse.dtype == torch.float32
-  assert np.abs(lse.cpu().numpy() - lref).max() < 2e-3
+  assert np.abs(lse.cpu().numpy() - lref).max() < 2e-4
 
 
 def test_explicit_scale_and_large_amplitude():
@@ -218,11 +218,11 @@ def test_dropout_matches_philox_oracle(p):
   q, k, v = _mk(1, 2, 2, 130, 203, 320, torch.bfloat16)
   seed, offset = 1234567, 40
   o, lse = torch.ops.ffpa_attn._fwd_cuda(q, k, v, q.new_empty(0), 0, 1, 0, 320 ** -0.5, p, seed, offset, True,
-                                         False, 0, 0, 0, 0, 0, False, 256, False, 256)
+                                         False, 0, 0, 0, 1, 0, False, 256, False, 256)
   torch.cuda.synchronize()
   ref, lref = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), dropout_p=p, philox_seed=seed, philox_offset=offset)
   _check(o, ref, 4e-2, "dropout")  # tests/test_ffpa_fwd.py:343-414 tolerance
-  assert np.abs(lse.cpu().numpy() - lref).max() < 2e-3
+  assert np.abs(lse.cpu().numpy() - lref).max() < 2e-4
 
 
 def test_dropout_through_public_api_advances_generator():
@@ -444,7 +444,7 @@ def test_decode_like_shapes_use_kv_splits(Nq, Nkv, Hq, Hkv, causal):
   for h in hs:
     ref, lref = orc.attention_fwd(q[:, h:h + 1].cpu(), k[:, h // g:h // g + 1].cpu(), v[:, h // g:h // g + 1].cpu(), causal=causal)
     assert np.abs(o[:, h:h + 1].float().cpu().numpy() - ref).max() < 1e-2
-    assert np.abs(lse[:, h:h + 1].cpu().numpy() - lref).max() < 2e-3
+    assert np.abs(lse[:, h:h + 1].cpu().numpy() - lref).max() < 2e-4
 
 
 def test_kv_split_with_bias_and_dropout_matches_oracle():
@@ -455,7 +455,7 @@ def test_kv_split_with_bias_and_dropout_matches_oracle():
   _check(out, ref, 2e-2, "split+bias")
   seed, offset = 99, 12
   o, _ = torch.ops.ffpa_attn._fwd_cuda(q, k, v, q.new_empty(0), 0, 1, 0, 256 ** -0.5, 0.25, seed, offset, True, False,
-                                       0, 0, 0, 0, 0, False, 256, False, 256)
+                                       0, 0, 0, 1, 0, False, 256, False, 256)
   torch.cuda.synchronize()
   ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu(), dropout_p=0.25, philox_seed=seed, philox_offset=offset)
   _check(o, ref, 4e-2, "split+dropout")

@@ -280,7 +280,7 @@ def test_fake_op_registered_for_compile():
 
   q = torch.empty(1, 2, 16, 64, dtype=torch.bfloat16, device="meta")
   o, lse = torch.ops.ffpa_attn._fwd_cuda(q, q, q, q.new_empty(0), 0, 1, 0, 0.125, 0.0, 0, 0, True, False,
-                                         0, 0, 0, 0, 0, False, 256, False, 256)
+                                         0, 0, 0, 1, 0, False, 256, False, 256)
   assert o.shape == q.shape and lse.shape == (1, 2, 16) and lse.dtype == torch.float32
 
 

@@ -130,3 +130,73 @@ def test_flops_formula():
   assert orc.attn_flops(1, 1, 4, 4, 8, causal=True) == 4.0 * 8 * 10
   assert orc.attn_flops(1, 1, 2, 4, 8, causal=True) == 4.0 * 8 * (3 + 4)
   assert orc.attn_flops(2, 4, 16, 16, 64, mode="bwd") == 2.5 * orc.attn_flops(2, 4, 16, 16, 64)
+
+
+# ---- FP8 oracle (oracle/fp8_oracle.py): pinned on e4m3 known answers, the reference's own acceptance bounds
+# ---- versus exact attention (/root/reference/tests/test_ffpa_fp8.py:56-86, 238-251) and algebraic identities
+def test_e4m3_rounding_known_answers():
+  from oracle import fp8_oracle as f8
+
+  x = np.array([0.0, 1.0, 1.0625, 1.1875, 447.0, 448.0, 449.0, 1e6, -1e6, 2.0 ** -9, 2.0 ** -10, 0.3, -0.3, 17.0, 25.0],
+               dtype=np.float32)
+  #            ties-to-even: 1.0625 -> 1.0 (mantissa step 0.125), 1.1875 -> 1.25; saturation at 448; subnormal step 2^-9
+  want = np.array([0.0, 1.0, 1.0, 1.25, 448.0, 448.0, 448.0, 448.0, -448.0, 2.0 ** -9, 0.0, 0.3125, -0.3125, 16.0, 24.0],
+                  dtype=np.float32)
+  assert np.array_equal(f8.e4m3_round(x), want)
+  assert f8.e4m3_bits(np.array([448.0, -448.0, 1.0, 0.0], dtype=np.float32)).tolist() == [0x7E, 0xFE, 0x38, 0x00]
+
+
+def test_fp8_quantiser_contract():
+  """quantize_fp8.cuh:67-168: one scale per (b, h, 128-row block) = amax / 448, the block's largest magnitude maps
+  to +-448 exactly, an all-zero block gets scale 0 and zeros (inv_s = 0 branch), tails use the rows that exist."""
+  from oracle import fp8_oracle as f8
+
+  rng = np.random.default_rng(0)
+  x = rng.standard_normal((2, 3, 300, 64)).astype(np.float32)
+  x[0, 0, 128:256] = 0.0
+  x8, s = f8.quantize_per_block(x)
+  assert s.shape == (2, 3, 3)
+  assert s[0, 0, 1] == 0.0 and np.all(x8[0, 0, 128:256] == 0)
+  for t in range(3):
+    blk = x[1, 2, t * 128:(t + 1) * 128]
+    assert np.isclose(s[1, 2, t], np.abs(blk).max() / 448.0, rtol=1e-6)
+    assert np.abs(x8[1, 2, t * 128:(t + 1) * 128]).max() == 448.0
+  deq = x8 * np.repeat(s, 128, axis=2)[:, :, :300, None]
+  assert np.abs(deq - x).max() <= np.abs(x).max() / 16 + 1e-6   # e4m3: 3 mantissa bits -> relative step 2^-4 at most
+
+
+@pytest.mark.parametrize("causal,smooth_k", [(False, True), (False, False), (True, True)])
+def test_fp8_oracle_meets_reference_bounds(causal, smooth_k):
+  """The quantised restatement stays inside the bounds the reference holds its FP8 kernels to versus exact fp32
+  attention on randn * 0.5 inputs: O 4e-2 dense / 1e-1 causal, LSE 5e-2 (tests/test_ffpa_fp8.py:63-65, 71, 86, 251)."""
+  from oracle import fp8_oracle as f8
+
+  torch.manual_seed(0)
+  B, Hq, Hkv, Nq, Nkv, D = 1, 4, 2, 256, 384, 128
+  q = (torch.randn(B, Hq, Nq, D) * 0.5).to(torch.bfloat16)
+  k = (torch.randn(B, Hkv, Nkv, D) * 0.5 + 0.75).to(torch.bfloat16)   # a channel mean smooth-K can remove
+  v = (torch.randn(B, Hkv, Nkv, D) * 0.5).to(torch.bfloat16)
+  o8, lse8, aux = f8.fp8_attention_fwd(q, k, v, causal=causal, smooth_k=smooth_k)
+  ref, lse = orc.attention_fwd(q, k, v, causal=causal)
+  assert np.abs(o8 - ref).max() < (1e-1 if causal else 4e-2)
+  assert np.abs(lse8 - lse).max() < 5e-2
+  assert aux["q8"].shape == (B, Hq, Nq, D) and aux["ks"].shape == (B, Hkv, 3)
+
+
+def test_fp8_smooth_k_identities():
+  """Softmax is shift invariant: subtracting mean_seq(K) changes neither O nor (after the q.km correction) the LSE
+  beyond quantisation noise, and it shrinks the K scales when K has a large common offset (smooth_k.cuh:8-16)."""
+  from oracle import fp8_oracle as f8
+
+  torch.manual_seed(1)
+  q = (torch.randn(1, 2, 128, 64) * 0.5).to(torch.float16)
+  k = (torch.randn(1, 2, 256, 64) * 0.25 + 1.5).to(torch.float16)
+  v = (torch.randn(1, 2, 256, 64) * 0.5).to(torch.float16)
+  o_s, lse_s, a_s = f8.fp8_attention_fwd(q, k, v, smooth_k=True)
+  o_n, lse_n, a_n = f8.fp8_attention_fwd(q, k, v, smooth_k=False)
+  ref, lse = orc.attention_fwd(q, k, v)
+  assert a_s["ks"].max() < 0.5 * a_n["ks"].max()
+  assert np.abs(o_s - ref).max() < np.abs(o_n - ref).max() + 1e-3
+  # the correction term is scale * qs * dot(Q8_row, km): the QUANTISED query against a mean of magnitude 1.5 over 64
+  # channels, so its own rounding error is what bounds the LSE here (the sm_100a kernel uses the unquantised row)
+  assert np.abs(o_s - ref).max() < 4e-2 and np.abs(lse_s - lse).max() < 1e-1

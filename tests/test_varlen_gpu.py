@@ -43,7 +43,7 @@ def test_varlen_forward_lse_and_backward(causal, D):
     ref, lref = orc.attention_fwd(qb, kb, vb, causal=causal)
     got = out[sq].transpose(0, 1)[None].float().cpu().numpy()
     assert np.abs(got - ref).max() < 2e-2
-    assert np.abs(lse[:, sq].cpu().numpy() - lref[0]).max() < 2e-3
+    assert np.abs(lse[:, sq].cpu().numpy() - lref[0]).max() < 2e-4
     assert np.abs(og[sq].transpose(0, 1)[None].detach().float().cpu().numpy() - ref).max() < 2e-2
     dob = d_o[sq].transpose(0, 1)[None].cpu()
     rq, rk, rv, _ = orc.attention_bwd(qb, kb, vb, dob, causal=causal)
@@ -99,7 +99,7 @@ def test_varlen_single_launch_many_sequences_and_graph_capture():
     ref, lref = orc.attention_fwd(q[sq].transpose(0, 1)[None].cpu(), k[sk].transpose(0, 1)[None].cpu(),
                                   v[sk].transpose(0, 1)[None].cpu())
     assert np.abs(out[sq].transpose(0, 1)[None].float().cpu().numpy() - ref).max() < 1e-2
-    assert np.abs(lse[:, sq].cpu().numpy() - lref[0]).max() < 2e-3
+    assert np.abs(lse[:, sq].cpu().numpy() - lref[0]).max() < 2e-4
   # graph capture: nothing on the path synchronises
   g = torch.cuda.CUDAGraph()
   static_out = None
@@ -191,7 +191,7 @@ def test_varlen_lse_output_is_differentiable(causal):
     ref_lse = torch.logsumexp(sc, dim=-1)
     ref_out = torch.softmax(sc, dim=-1) @ v32
     ((ref_out * d_o[s].float().transpose(0, 1)).sum() + (ref_lse * w[:, s]).sum()).backward()
-    assert (lse[:, s] - ref_lse).abs().max().item() < 2e-3
+    assert (lse[:, s] - ref_lse).abs().max().item() < 2e-4
     for got, want, name in ((qg.grad[s], q32.grad, "dQ"), (kg.grad[s], k32.grad, "dK"), (vg.grad[s], v32.grad, "dV")):
       err = (got.float().transpose(0, 1) - want).abs().max().item()
       assert err < 5e-2 * max(1.0, want.abs().max().item()), f"{name} seq {b}: {err}"
