@@ -596,27 +596,42 @@ def run_also(args, dev, peaks):
   the same-box A/B against the reference's GPU backends (subprocess: both packages register the same torch ops)."""
   import ffpa_attn
 
-  also = {}
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    _nv = pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0)
+    sm_clock = lambda: int(pynvml.nvmlDeviceGetClockInfo(_nv, pynvml.NVML_CLOCK_SM))  # noqa: E731
+  except Exception:  # noqa: BLE001
+    sm_clock = lambda: None  # noqa: E731
+  also = {"protocol": "per workload: 1.5 s idle (so every line starts from the same clock state as the headline's K-step "
+                      "burst), 2 warm-up steps, 10 timed steps (5 for backward kinds), CUDA events"}
   names = [n for n in ("c2_bwd", "c3_fwd_bwd", "c3_gqa_causal_fwd_hq32hkv8n4096d512", "c4_fp8_fwd", "d320_self_fwd",
                        "d768_self_fwd", "d1024_self_fwd") if n != args.workload]
   for name in names:
     wl = WORKLOADS[name]
     try:
       W = Workload(wl, dev, 7)
+      torch.cuda.synchronize()
+      time.sleep(1.5)
       ms = time_steps(W.step, 10 if wl["kind"] in ("fwd", "fp8_fwd") else 5, 2)
+      mhz = sm_clock()
       mult = 2.0 if wl["kind"] == "fp8_fwd" else 1.0
       rec = {"metric": METRIC[wl["kind"]], "ms_per_step": ms, "value": W.flops / ms * 1e-9, "unit": "TFLOP/s",
-             "peak": peaks["burst"] * mult, "frac": W.flops / ms * 1e-9 / (peaks["burst"] * mult)}
+             "peak": peaks["burst"] * mult, "frac": W.flops / ms * 1e-9 / (peaks["burst"] * mult), "sm_mhz_after": mhz}
       if name == "c2_bwd":
         # the O(N)-memory backward (three recompute kernels) next to the default (score stash from free memory)
         be = ffpa_attn.CUDABackend(bwd_min_workspace=True)
         o = ffpa_attn.ffpa_attn_func(W.qg, W.kg, W.vg, backend=be)
+        torch.cuda.synchronize()
+        time.sleep(1.5)
         ms_r = time_steps(lambda: torch.autograd.grad(o, (W.qg, W.kg, W.vg), W.d_o, retain_graph=True), 5, 2)
         rec["min_workspace_ms"] = ms_r
         rec["min_workspace_value"] = W.flops / ms_r * 1e-9
         del o
       if name == "c4_fp8_fwd":
         W.kw.pop("forward_backend")
+        torch.cuda.synchronize()
+        time.sleep(1.5)
         ms16 = time_steps(W.step, 10, 2)
         rec["bf16_kernel_ms_same_inputs"] = ms16
         rec["fp8_speedup_over_bf16_kernel"] = ms16 / ms

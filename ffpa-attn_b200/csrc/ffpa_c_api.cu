@@ -277,10 +277,10 @@ static int check_fwd(const ffpa_fwd_params* p) {
 }
 
 // scratch of ONE kernel-family stage over these sizes
-static uint64_t fwd_stage_workspace(const ffpa_fwd_params& p, int fp8_bits) {
+static uint64_t fwd_stage_workspace(const ffpa_fwd_params& p, int fp8_bits, uint64_t cap_bytes) {
   if (p.cu_seqlens_q) return 0;
-  if (fp8_bits) return fwd_fp8_workspace_bytes(p.batch, p.heads_q, p.heads_kv, p.seqlen_q, p.seqlen_kv, p.head_dim);
-  return fwd_split_workspace_bytes(p.batch, p.heads_q, p.seqlen_q, p.seqlen_kv, p.head_dim);
+  if (fp8_bits) return fwd_fp8_workspace_bytes(p.batch, p.heads_q, p.heads_kv, p.seqlen_q, p.seqlen_kv, p.head_dim);   // required
+  return fwd_split_workspace_bytes(p.batch, p.heads_q, p.heads_kv, p.seqlen_q, p.seqlen_kv, p.head_dim, cap_bytes);   // optional
 }
 
 // FP8 hybrid (/root/reference/csrc/cuffpa/launch.cuh:30-58, 341-374): stage 1 = rows [0, n_early) on the fp16/bf16
@@ -339,14 +339,14 @@ int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream) {
   return fwd_one(late, fp8_bits, st);
 }
 
-uint64_t ffpa_b200_fwd_workspace_bytes_p(const ffpa_fwd_params* p) {
+uint64_t ffpa_b200_fwd_workspace_bytes_p(const ffpa_fwd_params* p, uint64_t cap_bytes) {
   if (!p || p->batch <= 0 || p->heads_q <= 0 || p->heads_kv <= 0 || p->seqlen_q <= 0 || p->seqlen_kv <= 0 || p->head_dim <= 0) return 0;
   int fp8_bits = 0;
   if (resolve_impl(*p, &fp8_bits)) return 0;
-  if (!hybrid_applies(*p, fp8_bits)) return fwd_stage_workspace(*p, fp8_bits);
+  if (!hybrid_applies(*p, fp8_bits)) return fwd_stage_workspace(*p, fp8_bits, cap_bytes);
   ffpa_fwd_params early, late;
   hybrid_stages(*p, &early, &late);
-  const uint64_t a = fwd_stage_workspace(early, 0), b = late.seqlen_q > 0 ? fwd_stage_workspace(late, fp8_bits) : 0;
+  const uint64_t a = fwd_stage_workspace(early, 0, cap_bytes), b = late.seqlen_q > 0 ? fwd_stage_workspace(late, fp8_bits, cap_bytes) : 0;
   return a > b ? a : b;
 }
 

@@ -48,31 +48,46 @@ int fwd_kv_splits(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_
 
 // Replay path for head dims > 768 (ffpa_fwd_replay_sm100.cuh): pass 0 stores its 16-bit P tiles, the per-tile O
 // rescale factors and 1 / rowsum so the second O slab is a GEMM instead of a second Q K^T + softmax pass.
-// FFPA_FWD_REPLAY=0 disables it, FFPA_FWD_REPLAY_MAX_GB (default 20) bounds the scratch (beyond: two passes).
-struct ReplayPlan { uint64_t p_bytes = 0, f_bytes = 0, inv_bytes = 0; int n_mt_even = 0, nk_pad = 0; uint64_t total() const { return p_bytes + f_bytes + inv_bytes; } };
-static ReplayPlan replay_plan(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
+// The scratch is O(Nq * Nkv) per head, so it is planned from the bytes on offer (`avail`: the caller's cap when
+// sizing, the granted workspace at launch): the whole problem if it fits, else (batch element, KV-head range) chunks
+// that run one after the other through the same scratch (each must still fill the machine), else the two-pass
+// kernel (no scratch). FFPA_FWD_REPLAY=0 disables the path.
+struct ReplayPlan {
+  uint64_t p_bytes = 0, f_bytes = 0, inv_bytes = 0;
+  int n_mt_even = 0, nk_pad = 0;
+  int chunk_hkv = 0;
+  bool chunked = false;
+  uint64_t total() const { return p_bytes + f_bytes + inv_bytes; }
+};
+static ReplayPlan replay_sizes(uint64_t bh, int seqlen_q, int seqlen_kv) {
   ReplayPlan pl;
-  const int nqk = (head_dim + 63) / 64, dvp = ((nqk * 64 + 127) / 128) * 128;
-  if (dvp <= 768) return pl;
-  if (env_off("FFPA_FWD_REPLAY")) return pl;
-  const double cap = env_gb("FFPA_FWD_REPLAY_MAX_GB", 20.0) * 1073741824.0;
-  const uint64_t bh = (uint64_t)batch * heads_q;
-  const int n_mt_even = (((seqlen_q + 127) / 128) + 1) & ~1, nk_pad = (seqlen_kv + 255) / 256 * 256;
-  const uint64_t p_bytes = bh * n_mt_even * 128ull * nk_pad * 2;
-  const uint64_t f_bytes = (bh * n_mt_even * (uint64_t)(nk_pad / 128) * 128 * 4 + 255) / 256 * 256;
-  const uint64_t inv_bytes = (bh * n_mt_even * 128 * 4 + 255) / 256 * 256;
-  if ((double)(p_bytes + f_bytes + inv_bytes) > cap) return pl;
-  pl.p_bytes = p_bytes; pl.f_bytes = f_bytes; pl.inv_bytes = inv_bytes; pl.n_mt_even = n_mt_even; pl.nk_pad = nk_pad;
+  pl.n_mt_even = (((seqlen_q + 127) / 128) + 1) & ~1;
+  pl.nk_pad = (seqlen_kv + 255) / 256 * 256;
+  pl.p_bytes = bh * pl.n_mt_even * 128ull * pl.nk_pad * 2;
+  pl.f_bytes = (bh * pl.n_mt_even * (uint64_t)(pl.nk_pad / 128) * 128 * 4 + 255) / 256 * 256;
+  pl.inv_bytes = (bh * pl.n_mt_even * 128 * 4 + 255) / 256 * 256;
   return pl;
 }
-
-uint64_t fwd_replay_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
-  const ReplayPlan rp = replay_plan(batch, heads_q, seqlen_q, seqlen_kv, head_dim);
-  return rp.total() > 0 ? rp.total() + 256 : 0;
+static ReplayPlan replay_plan(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim, uint64_t avail) {
+  const int nqk = (head_dim + 63) / 64, dvp = ((nqk * 64 + 127) / 128) * 128;
+  if (dvp <= 768 || heads_kv <= 0) return ReplayPlan{};
+  if (env_off("FFPA_FWD_REPLAY")) return ReplayPlan{};
+  ReplayPlan whole = replay_sizes((uint64_t)batch * heads_q, seqlen_q, seqlen_kv);
+  if (whole.total() + 256 <= avail) { whole.chunk_hkv = heads_kv; return whole; }
+  const int group = heads_q / heads_kv, n_mt = (seqlen_q + 127) / 128;
+  for (int hc = heads_kv; hc >= 1; --hc) {
+    if (hc == heads_kv && batch == 1) continue;   // that is the whole problem
+    ReplayPlan pl = replay_sizes((uint64_t)hc * group, seqlen_q, seqlen_kv);
+    if (pl.total() + 256 > avail) continue;
+    if ((int64_t)hc * group * n_mt < sm_count() / 2) break;   // a chunk must still fill the machine
+    pl.chunk_hkv = hc; pl.chunked = true;
+    return pl;
+  }
+  return ReplayPlan{};
 }
 
-uint64_t fwd_split_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim) {
-  const ReplayPlan rp = replay_plan(batch, heads_q, seqlen_q, seqlen_kv, head_dim);
+uint64_t fwd_split_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim, uint64_t cap_bytes) {
+  const ReplayPlan rp = replay_plan(batch, heads_q, heads_kv, seqlen_q, seqlen_kv, head_dim, cap_bytes);
   if (rp.total() > 0) return rp.total() + 256;
   const int s = fwd_kv_splits(batch, heads_q, seqlen_q, seqlen_kv, head_dim);
   if (s <= 1) return 0;
@@ -129,7 +144,7 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   kp.total_k = a.total_k;
   if (!varlen) {
     const int sp = fwd_kv_splits(a.batch, a.heads_q, a.seqlen_q, a.seqlen_kv, D);
-    const uint64_t need = fwd_split_workspace_bytes(a.batch, a.heads_q, a.seqlen_q, a.seqlen_kv, D);
+    const uint64_t need = fwd_split_workspace_bytes(a.batch, a.heads_q, a.heads_kv, a.seqlen_q, a.seqlen_kv, D, 0);
     if (sp > 1 && a.workspace != nullptr && a.workspace_bytes >= need && (reinterpret_cast<uintptr_t>(a.workspace) & 15u) == 0) {
       const uint64_t rows = (uint64_t)a.batch * a.heads_q * a.seqlen_q;
       kp.kv_splits = sp;
@@ -138,9 +153,32 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
     }
   }
   // replay path (head dims > 768): one softmax pass that stores P / rescale factors / 1/rowsum, then a GEMM
-  const ReplayPlan rp = varlen ? ReplayPlan{} : replay_plan(a.batch, a.heads_q, a.seqlen_q, a.seqlen_kv, D);
-  const bool use_replay = rp.total() > 0 && a.workspace != nullptr && a.workspace_bytes >= rp.total() &&
-                          (reinterpret_cast<uintptr_t>(a.workspace) & 255u) == 0;
+  const bool ws_ok = a.workspace != nullptr && (reinterpret_cast<uintptr_t>(a.workspace) & 255u) == 0;
+  const ReplayPlan rp = (varlen || !ws_ok) ? ReplayPlan{}
+                                           : replay_plan(a.batch, a.heads_q, a.heads_kv, a.seqlen_q, a.seqlen_kv, D, a.workspace_bytes);
+  if (rp.chunked && a.bias_kind == FFPA_BIAS_NONE && !(a.dropout_p > 0.f)) {
+    // the stash of the whole problem does not fit the scratch: (batch element, KV-head range) chunks, one after the
+    // other through the same scratch (stream order serialises them); each chunk is an ordinary dense sub-problem
+    const int group = a.heads_q / a.heads_kv;
+    auto off = [](const void* p, int64_t elems) { return static_cast<const void*>(static_cast<const uint8_t*>(p) + 2 * elems); };
+    const int64_t lse_bh = a.lse_bh_stride > 0 ? a.lse_bh_stride : a.seqlen_q;
+    for (int b = 0; b < a.batch; ++b)
+      for (int hk0 = 0; hk0 < a.heads_kv; hk0 += rp.chunk_hkv) {
+        const int hc = (a.heads_kv - hk0) < rp.chunk_hkv ? (a.heads_kv - hk0) : rp.chunk_hkv;
+        const int hq0 = hk0 * group;
+        ffpa_fwd_params s = a;
+        s.batch = 1; s.heads_kv = hc; s.heads_q = hc * group;
+        s.q = off(a.q, b * a.q_stride[0] + hq0 * a.q_stride[1]);
+        s.o = const_cast<void*>(off(a.o, b * a.o_stride[0] + hq0 * a.o_stride[1]));
+        s.k = off(a.k, b * a.k_stride[0] + hk0 * a.k_stride[1]);
+        s.v = off(a.v, b * a.v_stride[0] + hk0 * a.v_stride[1]);
+        if (a.lse) s.lse = a.lse + ((int64_t)b * a.heads_q + hq0) * lse_bh;
+        s.lse_bh_stride = lse_bh;
+        if (int rc = launch_fwd_sm100(s, stream)) return rc;
+      }
+    return FFPA_OK;
+  }
+  const bool use_replay = rp.total() > 0 && !rp.chunked;
   kp.stash_p = nullptr; kp.stash_f = nullptr; kp.stash_inv = nullptr;
   kp.nk_pad = rp.nk_pad; kp.n_mt_even = rp.n_mt_even;
   kp.n_pass = npass;

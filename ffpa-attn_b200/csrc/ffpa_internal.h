@@ -122,9 +122,9 @@ int launch_bwd_sm100(const ffpa_bwd_params& a, cudaStream_t stream);
 // fp8_bits: 1 enable | 2 smooth-K | 4 smooth-V | 8 per-channel V scales
 int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, int fp8_bits, cudaStream_t stream);
 int fwd_kv_splits(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim);  // 1 = no split
-uint64_t fwd_split_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim);
+// optional forward scratch not above cap_bytes: replay stash (head dims > 768, chunked when needed) or KV-split partials
+uint64_t fwd_split_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim, uint64_t cap_bytes);
 uint64_t fwd_fp8_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv, int head_dim);
-uint64_t fwd_replay_workspace_bytes(int batch, int heads_q, int seqlen_q, int seqlen_kv, int head_dim);
 // recommended backward scratch not above max(cap, minimum): adds the stash buffers (chunked when needed)
 uint64_t bwd_workspace_bytes(int batch, int heads_q, int heads_kv, int seqlen_q, int seqlen_kv,
                              int head_dim, uint64_t cap_bytes);

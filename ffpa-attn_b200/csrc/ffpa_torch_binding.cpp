@@ -91,6 +91,29 @@ void fill_fwd_sizes(ffpa_fwd_params& p, const Tensor& Q, const Tensor& K) {
   p.heads_kv = (int32_t)K.size(1); p.seqlen_kv = (int32_t)K.size(2);
 }
 
+// Scratch policy: the stash path (5 GEMM passes instead of 8) trades O(Nq*Nkv) scratch for time. The scratch is
+// BOUNDED: at most FFPA_BWD_STASH_MAX_GB (default 2.5 GiB -- measured on B200, profiles/r02_bwd_cap_sweep.md: a problem
+// cut into (batch, KV-head) chunks that fit 2.25 GiB runs within 1-4 % of the unbounded stash, B=4 C2 960 vs 959
+// TFLOP/s) and never more than half of (free device memory + the allocator's cached blocks). `min_workspace`
+// (CUDABackend(bwd_min_workspace=True)) or FFPA_BWD_STASH=0 asks for the O(N) plan (three recompute kernels), and an
+// allocation failure falls back to it.
+uint64_t scratch_cap(const Tensor& like, const char* env_name) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+  uint64_t cached = 0;
+  try {
+    const auto st = c10::cuda::CUDACachingAllocator::getDeviceStats(like.device().index());
+    const int64_t r = st.reserved_bytes[0].current, a = st.allocated_bytes[0].current;
+    if (r > a) cached = (uint64_t)(r - a);
+  } catch (...) {
+  }
+  uint64_t cap = ((uint64_t)free_b + cached) / 2;
+  const char* g = std::getenv(env_name);
+  const double gb = (g ? atof(g) : 2.5) * 1073741824.0;
+  if (gb >= 0 && (double)cap > gb) cap = (uint64_t)gb;
+  return cap;
+}
+
 // ---------------------------------------------------------------------------------------------
 // ffpa_attn_forward -- signature of ffpa_api.cc:86-96; writes O and softmax_lse in place
 // ---------------------------------------------------------------------------------------------
@@ -151,7 +174,9 @@ void ffpa_attn_forward(Tensor Q, Tensor K, Tensor V, Tensor attn_bias, Tensor O,
   p.fp8_hybrid = fp8_hybrid; p.fp8_hybrid_n_early = (int32_t)fp8_hybrid_n_early;
 
   Tensor ws;
-  const uint64_t want = ffpa_b200_fwd_workspace_bytes_p(&p);
+  // optional O(Nq*Nkv) scratch (replay stash of head dims > 768) is bounded like the backward's: FFPA_FWD_REPLAY_MAX_GB
+  // (default 2.5 GiB) and half of the free memory; chunked over heads when the whole problem does not fit
+  const uint64_t want = ffpa_b200_fwd_workspace_bytes_p(&p, scratch_cap(Q, "FFPA_FWD_REPLAY_MAX_GB"));
   if (want > 0) {
     try {
       ws = alloc_bytes(want, Q);
@@ -169,28 +194,6 @@ void ffpa_attn_forward(Tensor Q, Tensor K, Tensor V, Tensor attn_bias, Tensor O,
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-// Scratch policy: the stash path (5 GEMM passes instead of 8) trades O(Nq*Nkv) scratch for time. It is granted
-// only from memory that is free anyway: at most half of (free device memory + the allocator's cached blocks),
-// optionally bounded by FFPA_BWD_STASH_MAX_GB; `min_workspace` (or FFPA_BWD_STASH=0) asks for the O(N) plan,
-// and an allocation failure falls back to it.
-uint64_t bwd_scratch_cap(const Tensor& like) {
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
-  uint64_t cached = 0;
-  try {
-    const auto st = c10::cuda::CUDACachingAllocator::getDeviceStats(like.device().index());
-    const int64_t r = st.reserved_bytes[0].current, a = st.allocated_bytes[0].current;
-    if (r > a) cached = (uint64_t)(r - a);
-  } catch (...) {
-  }
-  uint64_t cap = ((uint64_t)free_b + cached) / 2;
-  if (const char* g = std::getenv("FFPA_BWD_STASH_MAX_GB")) {
-    const double gb = atof(g) * 1073741824.0;
-    if (gb >= 0 && (double)cap > gb) cap = (uint64_t)gb;
-  }
-  return cap;
-}
-
 void backward_impl(const Tensor& Q, const Tensor& K, const Tensor& V, const Tensor& O, const Tensor& softmax_lse, const Tensor& dO,
                    Tensor& dQ, Tensor& dK, Tensor& dV, int64_t causal, double softmax_scale, const Tensor& attn_bias,
                    double dropout_p, int64_t philox_seed, int64_t philox_offset, const Tensor& d_bias, const Tensor& d_lse,
@@ -229,7 +232,7 @@ void backward_impl(const Tensor& Q, const Tensor& K, const Tensor& V, const Tens
     p.d_lse = d_lse.data_ptr<float>();
   }
   const uint64_t need_min = ffpa_b200_bwd_workspace_bytes_min_p(&p);
-  uint64_t want = min_workspace ? need_min : ffpa_b200_bwd_workspace_bytes_p(&p, bwd_scratch_cap(Q));
+  uint64_t want = min_workspace ? need_min : ffpa_b200_bwd_workspace_bytes_p(&p, scratch_cap(Q, "FFPA_BWD_STASH_MAX_GB"));
   Tensor ws;
   try {
     ws = alloc_bytes(want, Q);

@@ -85,7 +85,7 @@ typedef struct ffpa_fwd_params {
   float dropout_p;
   uint64_t philox_seed;
   uint64_t philox_offset;
-  /* scratch: ffpa_b200_fwd_workspace_bytes_p(params) bytes of 256-byte aligned device memory (FP8 copies and
+  /* scratch: ffpa_b200_fwd_workspace_bytes_p(params, cap) bytes of 256-byte aligned device memory (FP8 copies and
    * scales, KV-split partials of decode-like shapes, the replay stash of head dims > 768); may be NULL when
    * that function returns 0. Given less than asked for, paths that need no scratch run where they exist
    * (no KV split, two-pass instead of replay); the FP8 path fails with FFPA_ERR_INVALID_ARGUMENT. */
@@ -162,9 +162,12 @@ typedef struct ffpa_bwd_params {
 /* replaces ffpa_attn_forward (/root/reference/csrc/cuffpa/ffpa_api.cc:86-239) */
 int ffpa_b200_fwd(const ffpa_fwd_params* p, void* stream);
 
-/* scratch bytes ffpa_b200_fwd wants for exactly this call (pointers are not read; impl / fp8_* / hybrid /
- * sizes are). Larger than free memory is fine: pass what you can get, see `workspace` above. */
-uint64_t ffpa_b200_fwd_workspace_bytes_p(const ffpa_fwd_params* p);
+/* Scratch bytes ffpa_b200_fwd wants for exactly this call (pointers are not read; impl / fp8_* / hybrid / sizes
+ * are). The FP8 buffers are REQUIRED and returned whatever the cap; the optional scratch -- KV-split partials, and
+ * for head dims > 768 the O(Nq*Nkv)-per-head replay stash -- is planned to fit `cap_bytes`: the whole problem, else
+ * (batch, KV-head) chunks through one scratch, else none (two-pass kernel). The launcher plans from the bytes it is
+ * actually given, so any size is valid. */
+uint64_t ffpa_b200_fwd_workspace_bytes_p(const ffpa_fwd_params* p, uint64_t cap_bytes);
 
 /* replaces ffpa_attn_backward (/root/reference/csrc/cuffpa/ffpa_api.cc:242-263, a thrower there) */
 int ffpa_b200_bwd(const ffpa_bwd_params* p, void* stream);

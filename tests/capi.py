@@ -51,7 +51,7 @@ def load():
   lib.ffpa_b200_fwd.restype = ctypes.c_int
   lib.ffpa_b200_bwd.argtypes = [ctypes.POINTER(BwdParams), vp]
   lib.ffpa_b200_bwd.restype = ctypes.c_int
-  lib.ffpa_b200_fwd_workspace_bytes_p.argtypes = [ctypes.POINTER(FwdParams)]
+  lib.ffpa_b200_fwd_workspace_bytes_p.argtypes = [ctypes.POINTER(FwdParams), u64]
   lib.ffpa_b200_fwd_workspace_bytes_p.restype = u64
   lib.ffpa_b200_bwd_workspace_bytes_p.argtypes = [ctypes.POINTER(BwdParams), u64]
   lib.ffpa_b200_bwd_workspace_bytes_p.restype = u64

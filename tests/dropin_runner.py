@@ -213,4 +213,7 @@ for _name, _args in (
 ):
   case(_name)(lambda _a=_args: _ref_vs_ours(**_a))
 
+_out_dir = os.path.join(os.environ["FFPA_REPO_ROOT"], "gpurun_out")
+if os.path.isdir(_out_dir):   # scratch copy of the measurements (the test asserts on the line below)
+  json.dump(res, open(os.path.join(_out_dir, "dropin_results.json"), "w"), indent=1)
 print("DROPIN_JSON " + json.dumps(res))

@@ -266,7 +266,7 @@ def test_fp8_quantised_tiles_and_output_match_the_quantised_oracle(smooth_k):
   p.q, p.k, p.v, p.o, p.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr()
   for name, t in (("q_stride", q), ("k_stride", k), ("v_stride", v), ("o_stride", o)):
     setattr(p, name, (ctypes.c_int64 * 4)(*t.stride()))
-  need = lib.ffpa_b200_fwd_workspace_bytes_p(ctypes.byref(p))
+  need = lib.ffpa_b200_fwd_workspace_bytes_p(ctypes.byref(p), 0)
   ws = torch.zeros(need, dtype=torch.uint8, device=DEV)
   p.workspace, p.workspace_bytes = ws.data_ptr(), need
   rc = lib.ffpa_b200_fwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))

@@ -391,6 +391,29 @@ def test_replay_path_matches_two_pass_path_and_oracle(D, causal, shape, monkeypa
   del kw
 
 
+def test_replay_path_chunked_by_scratch_bound(monkeypatch):
+  """FFPA_FWD_REPLAY_MAX_GB bounds the O(Nq*Nkv) replay stash: a larger problem runs as (batch element, KV-head
+  range) chunks through one scratch and must equal the unchunked run bit for bit; below a machine-filling chunk
+  the two-pass kernel runs (same LSE and first slab bits, second slab to rounding)."""
+  import ffpa_attn
+
+  q, k, v = _mk(2, 8, 4, 2048, 2048, 1024, torch.bfloat16, seed=33)
+  n0 = ffpa_attn._C.launch_count()
+  o_full, lse_full = _lse(q, k, v, True)
+  assert ffpa_attn._C.launch_count() - n0 == 2
+  monkeypatch.setenv("FFPA_FWD_REPLAY_MAX_GB", "0.06")   # whole stash: 134 MB; 3 KV heads (6 query heads): 50 MB
+  n0 = ffpa_attn._C.launch_count()
+  o_c, lse_c = _lse(q, k, v, True)
+  assert ffpa_attn._C.launch_count() - n0 == 2 * 2 * 2   # 2 batch elements x KV-head chunks (3, 1) x 2 launches
+  assert torch.equal(o_c, o_full) and torch.equal(lse_c, lse_full)
+  monkeypatch.setenv("FFPA_FWD_REPLAY_MAX_GB", "0.001")
+  n0 = ffpa_attn._C.launch_count()
+  o_t, lse_t = _lse(q, k, v, True)
+  assert ffpa_attn._C.launch_count() - n0 == 1
+  assert torch.equal(lse_t, lse_full) and torch.equal(o_t[..., :512], o_full[..., :512])
+  assert (o_t.float() - o_full.float()).abs().max().item() < 4e-3
+
+
 def test_replay_path_with_bias_dropout_fp16_and_large_amplitude():
   """The replayed P is whatever pass 0 fed its MMA: bias and dropout included; large score amplitudes make
   the row max move often, i.e. many rescale events to replay."""

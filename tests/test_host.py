@@ -353,16 +353,20 @@ def test_forward_workspace_plan(lib, monkeypatch):
   and for FP8 hybrid the larger of its two stages."""
   f = lib.ffpa_b200_fwd_workspace_bytes_p
 
-  def F(*a, **kw):
-    return f(ctypes.byref(capi.fwd_sizes(*a, **kw)))
+  def F(*a, cap=1 << 40, **kw):
+    return f(ctypes.byref(capi.fwd_sizes(*a, **kw)), cap)
 
   assert F(1, 32, 32, 8192, 8192, 512) == 0
   assert F(1, 32, 32, 8192, 8192, 768) == 0
   need = F(1, 32, 32, 8192, 8192, 1024)
   if os.environ.get("FFPA_FWD_REPLAY", "1") != "0":
     assert 32 * 8192 * 8192 * 2 <= need <= 32 * 8192 * 8192 * 2 * 1.02   # P tiles + factors + 1/rowsum
+  if os.environ.get("FFPA_FWD_REPLAY", "1") != "0":
+    # bounded scratch: 2.5 GiB holds a machine-filling chunk of heads, 100 MB holds nothing -> two-pass kernel
+    assert 0 < F(1, 32, 32, 8192, 8192, 1024, cap=int(2.5 * 2 ** 30)) <= 2.5 * 2 ** 30
+    assert F(1, 32, 32, 8192, 8192, 1024, cap=100 << 20) == 0
   assert F(1, 32, 32, 1, 8192, 512) > 0     # decode: KV-split partials
-  fp8 = F(1, 32, 32, 8192, 8192, 256, impl=5)
+  fp8 = F(1, 32, 32, 8192, 8192, 256, impl=5, cap=0)   # required scratch: returned whatever the cap
   assert fp8 > 3 * 32 * 8192 * 256           # FP8: e4m3 copies of Q, K, V + scales
   hyb = F(1, 32, 32, 8192, 8192, 256, impl=5, causal=1, fp8_hybrid=1, fp8_hybrid_n_early=256)
   assert 0 < hyb <= fp8                      # stage 2 quantises 256 fewer query rows

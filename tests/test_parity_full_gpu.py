@@ -288,7 +288,10 @@ def test_c5_headdim_sweep_forward_every_head(D, replay, monkeypatch):
   o, lse = _run_fwd(q, k, v, False)
   torch.cuda.synchronize()
   if D == 1024:
-    assert ffpa_attn._C.launch_count() - n0 == (2 if replay else 1)
+    # replay: (softmax pass + GEMM) per chunk -- the 4.3 GB stash is cut into head chunks that fit the default
+    # 2.5 GiB scratch bound (FFPA_FWD_REPLAY_MAX_GB); two-pass: one launch
+    n = ffpa_attn._C.launch_count() - n0
+    assert (n >= 2 and n % 2 == 0) if replay else n == 1, n
   bound = v.float().abs().max().item() * _BF16_OPERAND_ULP
   _check_fwd_all_heads(q, k, v, False, o, lse, bound, _LSE_ABS_TOL, 0.99999, f"C5-D{D}")
 
