@@ -85,13 +85,12 @@ def measured_peaks():
   return {"burst": 1590.0, "sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
-def kernel_source_hash() -> str:
-  """sha of the kernel sources: a stored ncu traffic figure is only quoted for the sources it was captured from."""
+def kernel_source_hash(files) -> str:
+  """sha of the sources of one kernel: a stored ncu traffic figure is only quoted for the sources it was captured
+  from (tools/update_roofline_traffic.py writes the record together with the file list)."""
   h = hashlib.sha256()
-  csrc = os.path.join(PKG, "csrc")
-  for f in sorted(os.listdir(csrc)):
-    if f.endswith((".cu", ".cuh", ".h")):
-      h.update(open(os.path.join(csrc, f), "rb").read())
+  for f in sorted(files):
+    h.update(open(os.path.join(PKG, "csrc", f), "rb").read())
   return h.hexdigest()[:16]
 
 
@@ -103,7 +102,7 @@ def measured_traffic(workload: str):
     return None, "no capture"
   if not isinstance(rec, dict):
     return None, "no capture for this workload"
-  if rec.get("kernel_source_sha16") != kernel_source_hash():
+  if rec.get("kernel_source_sha16") != kernel_source_hash(rec.get("kernel_sources", [])):
     return None, f"capture {rec.get('capture')} is from other kernel sources (sha {rec.get('kernel_source_sha16')})"
   return rec.get("dram_bytes_per_launch"), rec.get("capture")
 
@@ -309,6 +308,9 @@ def main():
   ap.add_argument("--sustain-seconds", type=float, default=1.0)
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+  if os.environ.get("FFPA_BENCH_WATCHDOG_S"):   # debugging aid: dump every thread's stack and exit after N seconds
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ["FFPA_BENCH_WATCHDOG_S"]), exit=True)
 
   rank = int(os.environ.get("RANK", "0"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -603,17 +605,16 @@ def run_also(args, dev, peaks):
     sm_clock = lambda: int(pynvml.nvmlDeviceGetClockInfo(_nv, pynvml.NVML_CLOCK_SM))  # noqa: E731
   except Exception:  # noqa: BLE001
     sm_clock = lambda: None  # noqa: E731
-  also = {"protocol": "per workload: 1.5 s idle (so every line starts from the same clock state as the headline's K-step "
-                      "burst), 2 warm-up steps, 10 timed steps (5 for backward kinds), CUDA events"}
+  also = {"protocol": "per workload, back to back in one process: 5 warm-up steps, 10 timed steps (5 for backward kinds), CUDA "
+                      "events; sm_mhz_after = SM clock right after the timed steps (the GPU is warm: later lines run at lower "
+                      "clocks than the headline burst)"}
   names = [n for n in ("c2_bwd", "c3_fwd_bwd", "c3_gqa_causal_fwd_hq32hkv8n4096d512", "c4_fp8_fwd", "d320_self_fwd",
                        "d768_self_fwd", "d1024_self_fwd") if n != args.workload]
   for name in names:
     wl = WORKLOADS[name]
     try:
       W = Workload(wl, dev, 7)
-      torch.cuda.synchronize()
-      time.sleep(1.5)
-      ms = time_steps(W.step, 10 if wl["kind"] in ("fwd", "fp8_fwd") else 5, 2)
+      ms = time_steps(W.step, 10 if wl["kind"] in ("fwd", "fp8_fwd") else 5, 5)
       mhz = sm_clock()
       mult = 2.0 if wl["kind"] == "fp8_fwd" else 1.0
       rec = {"metric": METRIC[wl["kind"]], "ms_per_step": ms, "value": W.flops / ms * 1e-9, "unit": "TFLOP/s",
@@ -622,17 +623,13 @@ def run_also(args, dev, peaks):
         # the O(N)-memory backward (three recompute kernels) next to the default (score stash from free memory)
         be = ffpa_attn.CUDABackend(bwd_min_workspace=True)
         o = ffpa_attn.ffpa_attn_func(W.qg, W.kg, W.vg, backend=be)
-        torch.cuda.synchronize()
-        time.sleep(1.5)
-        ms_r = time_steps(lambda: torch.autograd.grad(o, (W.qg, W.kg, W.vg), W.d_o, retain_graph=True), 5, 2)
+        ms_r = time_steps(lambda: torch.autograd.grad(o, (W.qg, W.kg, W.vg), W.d_o, retain_graph=True), 5, 5)
         rec["min_workspace_ms"] = ms_r
         rec["min_workspace_value"] = W.flops / ms_r * 1e-9
         del o
       if name == "c4_fp8_fwd":
         W.kw.pop("forward_backend")
-        torch.cuda.synchronize()
-        time.sleep(1.5)
-        ms16 = time_steps(W.step, 10, 2)
+        ms16 = time_steps(W.step, 10, 5)
         rec["bf16_kernel_ms_same_inputs"] = ms16
         rec["fp8_speedup_over_bf16_kernel"] = ms16 / ms
       also[name] = rec

@@ -3,6 +3,15 @@
 #include "ffpa_fwd_fp8_sm100.cuh"
 
 namespace ffpa {
+namespace fp8 {
+#define FFPA_FP8_EXTERN(NB, BF, W) \
+  extern template int launch_fp8_variant<NB, BF, W>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const Fp8KernelParams&, int, cudaStream_t);
+FFPA_FP8_EXTERN(1, true, 2) FFPA_FP8_EXTERN(2, true, 2) FFPA_FP8_EXTERN(3, true, 2) FFPA_FP8_EXTERN(4, true, 2)
+FFPA_FP8_EXTERN(1, true, 4) FFPA_FP8_EXTERN(2, true, 4) FFPA_FP8_EXTERN(3, true, 4) FFPA_FP8_EXTERN(4, true, 4)
+FFPA_FP8_EXTERN(1, false, 2) FFPA_FP8_EXTERN(2, false, 2) FFPA_FP8_EXTERN(3, false, 2) FFPA_FP8_EXTERN(4, false, 2)
+FFPA_FP8_EXTERN(1, false, 4) FFPA_FP8_EXTERN(2, false, 4) FFPA_FP8_EXTERN(3, false, 4) FFPA_FP8_EXTERN(4, false, 4)
+#undef FFPA_FP8_EXTERN
+}  // namespace fp8
 
 static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
@@ -43,14 +52,16 @@ static bool make_map8(CUtensorMap* m, const void* base, int B, int H, int N, int
   return tmap::encode_sw128(m, const_cast<void*>(base), 1, 4, dims, str, box);
 }
 
-template <bool OUT_BF16>
+// softmax warpgroups per CTA: 4 (tiles round robin over four warpgroups) unless FFPA_FP8_NWG=2 asks for the
+// two-warpgroup variant (A/B knob; read once per process)
+template <bool OUT_BF16, int NWG>
 static int dispatch_nb(int nb, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                        const fp8::Fp8KernelParams& kp, int ncl, cudaStream_t s) {
   switch (nb) {
-    case 1: return fp8::launch_fp8_variant<1, OUT_BF16>(mq, mk, mv, kp, ncl, s);
-    case 2: return fp8::launch_fp8_variant<2, OUT_BF16>(mq, mk, mv, kp, ncl, s);
-    case 3: return fp8::launch_fp8_variant<3, OUT_BF16>(mq, mk, mv, kp, ncl, s);
-    case 4: return fp8::launch_fp8_variant<4, OUT_BF16>(mq, mk, mv, kp, ncl, s);
+    case 1: return fp8::launch_fp8_variant<1, OUT_BF16, NWG>(mq, mk, mv, kp, ncl, s);
+    case 2: return fp8::launch_fp8_variant<2, OUT_BF16, NWG>(mq, mk, mv, kp, ncl, s);
+    case 3: return fp8::launch_fp8_variant<3, OUT_BF16, NWG>(mq, mk, mv, kp, ncl, s);
+    case 4: return fp8::launch_fp8_variant<4, OUT_BF16, NWG>(mq, mk, mv, kp, ncl, s);
     default: return set_error(FFPA_ERR_UNSUPPORTED, "FP8 forward supports head_dim <= 512");
   }
 }
@@ -102,15 +113,10 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, int fp8_bits, cudaStream_t st
       fp8::k_colsum_kernel<true><<<nblk, 256, 0, stream>>>(a.k, ksum, a.k_stride[0], a.k_stride[1], a.k_stride[2], Hkv, Nkv, D, rpb);
     else
       fp8::k_colsum_kernel<false><<<nblk, 256, 0, stream>>>(a.k, ksum, a.k_stride[0], a.k_stride[1], a.k_stride[2], Hkv, Nkv, D, rpb);
-    const unsigned qblk = (unsigned)(((int64_t)B * Hq * Nq + 7) / 8);
-    if (a.dtype == FFPA_DTYPE_BF16)
-      fp8::q_dot_kmean_kernel<true><<<qblk, 256, 0, stream>>>(a.q, ksum, qkm, a.q_stride[0], a.q_stride[1], a.q_stride[2], B, Hq, Hkv, Nq, Nkv, D);
-    else
-      fp8::q_dot_kmean_kernel<false><<<qblk, 256, 0, stream>>>(a.q, ksum, qkm, a.q_stride[0], a.q_stride[1], a.q_stride[2], B, Hq, Hkv, Nq, Nkv, D);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "smooth-K pre-pass launch failed: %s", cudaGetErrorString(e));
     count_launch();
-    count_launch();
+    qa.qkm = qkm;   // q . mean_seq(K) per query row: emitted by the Q blocks of the quantiser
     qa.ksum = ksum;
   }
   // smooth-V (fp8_bits bit 2; reference knob fp8_smooth_v): quantise V - mean_seq(V), add the mean back to O
@@ -179,8 +185,12 @@ int launch_fwd_fp8_sm100(const ffpa_fwd_params& a, int fp8_bits, cudaStream_t st
   int ncl = sm_count() / 2;
   if (ncl > kp.n_items) ncl = kp.n_items;
   const int nb = (D + 127) / 128;
-  return a.dtype == FFPA_DTYPE_BF16 ? dispatch_nb<true>(nb, mq, mk, mv, kp, ncl, stream)
-                                    : dispatch_nb<false>(nb, mq, mk, mv, kp, ncl, stream);
+  const bool two = env_gb("FFPA_FP8_NWG", 4.0) == 2.0;
+  if (two)
+    return a.dtype == FFPA_DTYPE_BF16 ? dispatch_nb<true, 2>(nb, mq, mk, mv, kp, ncl, stream)
+                                      : dispatch_nb<false, 2>(nb, mq, mk, mv, kp, ncl, stream);
+  return a.dtype == FFPA_DTYPE_BF16 ? dispatch_nb<true, 4>(nb, mq, mk, mv, kp, ncl, stream)
+                                    : dispatch_nb<false, 4>(nb, mq, mk, mv, kp, ncl, stream);
 }
 
 }  // namespace ffpa

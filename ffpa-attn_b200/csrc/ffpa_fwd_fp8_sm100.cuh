@@ -23,10 +23,6 @@
 namespace ffpa {
 namespace fp8 {
 
-constexpr int kSoftmaxWarps = 8;
-constexpr int kMmaWarp = 8;
-constexpr int kTmaWarp = 9;
-constexpr int kThreads = 320;
 constexpr int kSmemLimit = 232448;
 constexpr float kLazyThreshold = 4.0f;   // /root/reference/csrc/cuffpa/common.cuh:14-18 (fp8)
 constexpr float kPScale = 28.0f;         // 448 / 2^kLazyThreshold
@@ -57,11 +53,16 @@ struct Fp8Cfg {
   static constexpr int NSLICE = DVP / 256;
   static constexpr int O_COLS = DVP / 2;
   static constexpr int KST = (NB + 1) / 2;         // 16 KB K stages ([64 keys x 256 d]) per KV tile
-  static constexpr int S_BASE = 256;
+  static constexpr int S_BASE = O_COLS;            // S stages follow the O accumulator in TMEM
   static constexpr int Q_BYTES = NB * 8192;
-  static constexpr int KSTG = 4;   // S (TMEM) / P (SMEM) pipeline depth (O_COLS <= 256 leaves 4 x 64 columns)
+  // S (TMEM) / P (SMEM) pipeline depth = every 64-column stage that fits behind O: 4 at head dims 257..512, 6 at
+  // head dims <= 256. Deeper than the number of softmax warpgroups matters: with depth == warpgroups the QK MMA of a
+  // warpgroup's NEXT tile can only be issued once that warpgroup has finished its current one (same S stage), so
+  // every warpgroup idles for a QK + PV + signalling round trip per tile (31 % of all warp samples sat in the
+  // s_full wait at C4, profiles/r02_fp8_c4_ncu.md).
+  static constexpr int KSTG = (512 - O_COLS) / 64 > 6 ? 6 : (512 - O_COLS) / 64;
   static constexpr int P_BYTES = KSTG * 8192;
-  static constexpr int kBudget = kSmemLimit - 5120;   // static smem: barriers, exchange buffers
+  static constexpr int kBudget = kSmemLimit - 8192;   // static smem: barriers, exchange buffers (4 softmax warpgroups)
   static constexpr int kAvail = (kBudget - Q_BYTES - P_BYTES) / 16384;
   static constexpr int NVS = (kAvail / 2) > 6 ? 6 : (kAvail / 2);    // 16 KB V stages ([128 keys x 128 d])
   static constexpr int NKS = (kAvail - NVS) > 8 ? 8 : (kAvail - NVS);
@@ -74,8 +75,8 @@ struct Barriers {
   uint64_t q_full, q_empty;
   uint64_t k_full[8], k_empty[8];
   uint64_t v_full[6], v_empty[6];
-  uint64_t s_full[4];
-  uint64_t p_full[4], p_empty[4];
+  uint64_t s_full[6];
+  uint64_t p_full[6], p_empty[6];
   uint64_t m_full[4];
 };
 
@@ -118,20 +119,28 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
   return pack_e4m3x2(a, b) | (pack_e4m3x2(c, d) << 16);
 }
 
-template <int NB, bool OUT_BF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// NWG softmax warpgroups (4 warps each) take KV tiles round robin (tile i -> warpgroup i % NWG); warps NWG*4 / NWG*4+1
+// are the MMA issuer / TMA producer. NWG = 4 keeps four warps per scheduler in four different phases of four different
+// tiles: the softmax of one tile is a chain of dependent waits (S ready -> TMEM load -> max -> SMEM exchange -> running
+// max of the previous tile -> exp2 -> P store), and with two warps per scheduler the issue slots sat idle 59 % of the
+// time while both waited (profiles/r02_fp8_c4_ncu.md).
+template <int NB, bool OUT_BF16, int NWG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 * NWG + 2) * 32, 1)
 ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const Fp8KernelParams p) {
   using Cfg = Fp8Cfg<NB>;
+  constexpr int kMmaWarp = 4 * NWG, kTmaWarp = 4 * NWG + 1;
+  static_assert(NWG == 2 || NWG == 4, "softmax warpgroups: 2 or 4");
+  static_assert(NWG <= Cfg::KSTG, "one S / P stage per warpgroup in flight");
   constexpr int CG = 2;
   constexpr uint32_t KS = Cfg::KSTG;
   constexpr int LA = Cfg::KSTG - 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ Barriers bars;
-  __shared__ float xchw[2][2][2][64];  // row-max exchange between the two lane halves: [wg][parity][kh][row]
+  __shared__ float xchw[NWG][2][2][64];  // row-max exchange between the two lane halves: [wg][parity][kh][row]
   __shared__ float mval[4][64];        // running row max, published per tile (ring of 4: a lagging warp of the
                                        // consumer warpgroup is at most one of its own tiles behind)
-  __shared__ float xl[4][64];          // end-of-item row-sum exchange
+  __shared__ float xl[2 * NWG][64];    // end-of-item row-sum exchange
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
@@ -152,9 +161,9 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     ptx::mbar_init(bar(bars.q_empty), 1);
     for (int i = 0; i < 8; ++i) { ptx::mbar_init(bar(bars.k_full[i]), 1); ptx::mbar_init(bar(bars.k_empty[i]), 1); }
     for (int i = 0; i < 6; ++i) { ptx::mbar_init(bar(bars.v_full[i]), 1); ptx::mbar_init(bar(bars.v_empty[i]), 1); }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 6; ++i) {
       ptx::mbar_init(bar(bars.s_full[i]), 1);
-      ptx::mbar_init(bar(bars.p_full[i]), kSoftmaxWarps);  // 4 warps of one warpgroup x 2 CTAs
+      ptx::mbar_init(bar(bars.p_full[i]), 8);  // 4 warps of one warpgroup x 2 CTAs
       ptx::mbar_init(bar(bars.p_empty[i]), 1);
     }
     for (int i = 0; i < 4; ++i) ptx::mbar_init(bar(bars.m_full[i]), 2);  // the two kh == 0 warps of the publishing warpgroup
@@ -287,14 +296,16 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncwarp();
   } else {
     // =========================================== softmax / correction / epilogue ================
-    // Two warpgroups work on ALTERNATE KV tiles (wg = tile parity), each thread owning one TMEM lane
-    // (row, 64-key half) of its tile. Tiles i and i+1 are therefore in different phases of
-    // load / max / exp2 / pack, so the MUFU pipe of one overlaps the ALU work of the other (with
-    // column-split warpgroups both sit in the same phase of the same tile, see
+    // NWG warpgroups work on DIFFERENT KV tiles (tile i -> warpgroup i % NWG), each thread owning one TMEM lane
+    // (row, 64-key half) of its tile. Tiles i .. i+NWG-1 are therefore in different phases of
+    // load / max / exp2 / pack, so the MUFU pipe of one overlaps the ALU work and the waits of the others (with
+    // column-split warpgroups all sit in the same phase of the same tile, see
     // profiles/r01_fwd_small_d_ncu.md). The only cross-warpgroup dependency is the running row max,
     // published through SMEM + an mbarrier right after a tile's max is known.
+    // The scores are read from TMEM twice -- once for the max, once (in two 32-column halves) for exp2 / pack -- so a
+    // thread never holds more than 32 of them: that is what lets 4 warpgroups fit the register file.
     const uint32_t t = threadIdx.x;
-    const uint32_t wg = t >> 7;               // tile parity handled by this warpgroup
+    const uint32_t wg = t >> 7;               // tiles i with i % NWG == wg
     const uint32_t lane128 = t & 127;
     const uint32_t row = lane128 & 63;
     const uint32_t kh = lane128 >> 6;         // 64-key half of the KV tile / column half of O
@@ -321,44 +332,49 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const float pc_base = vref > 0.f ? kPScale / vref : 0.f;
       float m_l = NEG_INF, l = 0.f;           // partial row sum of this thread, relative to m_l
 
-      for (int i = (int)wg; i < T; i += 2, ++uw) {
+      for (int i = (int)wg; i < T; i += NWG, ++uw) {
         const uint32_t gi = g + (uint32_t)i;
         const uint32_t sbuf = gi % KS;
         const uint32_t xb = uw & 1;
         const float mul = qs_c * __ldg(ksp + i);
         const float pc = pc_base * __ldg(vsp + i);
-        ptx::mbar_wait(bar(bars.s_full[sbuf]), (gi / KS) & 1);
-        ptx::tc_fence_after();
-        uint32_t sr[64];
-        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf, sr);
-        ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf + 32, sr + 32);
-        ptx::tmem_wait_ld();
-        float x[64];
+        const uint32_t s_addr = tmem + lane_base + Cfg::S_BASE + 64 * sbuf;
         const int key0 = i * 128 + 64 * (int)kh;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) x[j] = __uint_as_float(sr[j]);
         const bool tail = (i * 128 + 128 > p.seqlen_kv);
         const bool diag = p.causal && (i * 128 + 127 > q0 + (p.seqlen_kv - p.seqlen_q));
-        if (tail || diag) {
-          const int lim = p.causal ? (causal_lim < p.seqlen_kv - 1 ? causal_lim : p.seqlen_kv - 1) : p.seqlen_kv - 1;
+        const bool masked = tail || diag;
+        const int lim = p.causal ? (causal_lim < p.seqlen_kv - 1 ? causal_lim : p.seqlen_kv - 1) : p.seqlen_kv - 1;
+        ptx::mbar_wait(bar(bars.s_full[sbuf]), (gi / KS) & 1);
+        ptx::tc_fence_after();
+        // ---- pass 1: row max of this thread's 64 raw scores, 32 at a time
+        float tmax = NEG_INF;
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (key0 + j > lim) x[j] = NEG_INF;
-        }
-        float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
-        float mx2 = fmax3(x[6], x[7], x[8]), mx3 = fmax3(x[9], x[10], x[11]);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sr[32];
+          ptx::tmem_ld_x32(s_addr + 32 * half, sr);
+          ptx::tmem_wait_ld();
+          float x[32];
 #pragma unroll
-        for (int j = 12; j < 60; j += 12) {
-          mx0 = fmax3(mx0, x[j], x[j + 1]); mx1 = fmax3(mx1, x[j + 2], x[j + 3]);
-          mx2 = fmax3(mx2, x[j + 4], x[j + 5]); mx3 = fmax3(mx3, x[j + 6], x[j + 7]);
-          mx0 = fmax3(mx0, x[j + 8], x[j + 9]); mx1 = fmax3(mx1, x[j + 10], x[j + 11]);
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]);
+          if (masked) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (key0 + 32 * half + j > lim) x[j] = NEG_INF;
+          }
+          float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
+          float mx2 = fmax3(x[6], x[7], x[8]), mx3 = fmax3(x[9], x[10], x[11]);
+          mx0 = fmax3(mx0, x[12], x[13]); mx1 = fmax3(mx1, x[14], x[15]);
+          mx2 = fmax3(mx2, x[16], x[17]); mx3 = fmax3(mx3, x[18], x[19]);
+          mx0 = fmax3(mx0, x[20], x[21]); mx1 = fmax3(mx1, x[22], x[23]);
+          mx2 = fmax3(mx2, x[24], x[25]); mx3 = fmax3(mx3, x[26], x[27]);
+          mx0 = fmax3(mx0, x[28], x[29]); mx1 = fmax3(mx1, x[30], x[31]);
+          tmax = fmaxf(tmax, fmaxf(fmax3(mx0, mx1, mx2), mx3));
         }
-        mx2 = fmax3(mx2, x[60], x[61]); mx3 = fmax3(mx3, x[62], x[63]);
-        float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3) * mul;   // scaled (log2) domain
+        tmax *= mul;   // scaled (log2) domain
         xchw[wg][xb][kh][row] = tmax;
         ptx::named_bar_sync(1 + 2 * wg + rgrp, 64);
         tmax = fmaxf(tmax, xchw[wg][xb][kh ^ 1][row]);
-        // running max of tile i-1, published by the other warpgroup
+        // running max of tile i-1, published by the previous warpgroup
         float m_prev = NEG_INF;
         if (i > 0) {
           const uint32_t par = (uint32_t)(i - 1) & 3u;
@@ -378,17 +394,42 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         if (need_rescale) factor = exp2f(m_prev - m_use);
         const float cadd = (pc > 0.f ? log2f(pc) : 0.f) - m_safe;
         const float2 mul2 = make_float2(mul, mul), c2 = make_float2(cadd, cadd);
-        uint32_t pk[16];
+        // ---- pass 2: exp2 / row sum / e4m3 pack, 32 scores at a time, straight into the P tile
+        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((gi / KS) & 1) ^ 1);
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        // P8 tile: one 128-byte row per query row; this thread owns bytes [64 kh, 64 kh + 64)
+        const uint32_t prow = sP + sbuf * 8192 + row * 128;
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          const float2 a0 = ffma2(make_float2(x[j], x[j + 1]), mul2, c2);
-          const float2 a1 = ffma2(make_float2(x[j + 2], x[j + 3]), mul2, c2);
-          const float2 e0 = make_float2(exp2f(a0.x), exp2f(a0.y));
-          const float2 e1 = make_float2(exp2f(a1.x), exp2f(a1.y));
-          acc0 = fadd2(acc0, e0);
-          acc1 = fadd2(acc1, e1);
-          pk[j >> 2] = pack_e4m3x4(e0.x, e0.y, e1.x, e1.y);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sr[32];
+          ptx::tmem_ld_x32(s_addr + 32 * half, sr);
+          ptx::tmem_wait_ld();
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(sr[j]);
+          if (masked) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (key0 + 32 * half + j > lim) x[j] = NEG_INF;
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float2 a0 = ffma2(make_float2(x[j], x[j + 1]), mul2, c2);
+            const float2 a1 = ffma2(make_float2(x[j + 2], x[j + 3]), mul2, c2);
+            const float2 e0 = make_float2(exp2f(a0.x), exp2f(a0.y));
+            const float2 e1 = make_float2(exp2f(a1.x), exp2f(a1.y));
+            acc0 = fadd2(acc0, e0);
+            acc1 = fadd2(acc1, e1);
+            pk[j >> 2] = pack_e4m3x4(e0.x, e0.y, e1.x, e1.y);
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t addr = prow + (((4 * kh + 2 * half + c) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
+                         "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                         : "memory");
+          }
         }
         acc0 = fadd2(acc0, acc1);
         const float lsum = (acc0.x + acc0.y) * (pc > 0.f ? 1.f / pc : 0.f);
@@ -397,18 +438,6 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         l += lsum;
         m_l = m_use;
 
-        ptx::mbar_wait(bar(bars.p_empty[sbuf]), ((gi / KS) & 1) ^ 1);
-        {
-          // P8 tile: one 128-byte row per query row; this thread owns bytes [64 kh, 64 kh + 64)
-          const uint32_t prow = sP + sbuf * 8192 + row * 128;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t addr = prow + (((4 * kh + c) ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
-                         "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
-                         : "memory");
-          }
-        }
         if (__any_sync(0xffffffffu, need_rescale)) {
           // O may only be touched once PV of tile i-1 has retired; this warpgroup scales all columns
           ptx::mbar_wait(bar(bars.p_empty[(gi - 1) % KS]), ((gi - 1) / KS) & 1);
@@ -441,8 +470,9 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int j = 0; j < 4; ++j) pub[j] += (T > j) ? (uint32_t)((T - 1 - j) / 4 + 1) : 0u;
         const float l_fin = (m_l == NEG_INF) ? 0.f : l * exp2f(m_l - m_fin);
         xl[wg * 2 + kh][row] = l_fin;
-        ptx::named_bar_sync(5 + rgrp, 128);   // both warpgroups: nobody enters the next item before m_fin is read
-        const float l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
+        ptx::named_bar_sync(1 + 2 * NWG + rgrp, 64 * NWG);   // all warpgroups: nobody enters the next item before m_fin is read
+        float l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
+        if constexpr (NWG == 4) l_tot += (xl[4][row] + xl[5][row]) + (xl[6][row] + xl[7][row]);
         const uint32_t gl = g + (uint32_t)T - 1;
         ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
         ptx::tc_fence_after();
@@ -460,7 +490,7 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
         for (int s = 0; s < Cfg::NSLICE; ++s) {
 #pragma unroll 1
-          for (int c0 = (int)wg * 64; c0 < (int)(wg + 1) * 64; c0 += 32) {
+          for (int c0 = (int)wg * (128 / NWG); c0 < (int)(wg + 1) * (128 / NWG); c0 += 32) {
             uint32_t orr[32];
             ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c0, orr);
             ptx::tmem_wait_ld();
@@ -498,7 +528,7 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         ptx::tc_fence_before();
         // xl is reused by the next item: all four writers must be past their reads first
-        ptx::named_bar_sync(5 + rgrp, 128);
+        ptx::named_bar_sync(1 + 2 * NWG + rgrp, 64 * NWG);
         g += (uint32_t)T;
       }
     }
@@ -526,14 +556,24 @@ struct QuantArgs {
   const float* ksum;       // [B, Hkv, D] column sums of K over the sequence (smooth-K) or nullptr
   const float* vsum;       // [B, Hkv, D] column sums of V over the sequence (smooth-V) or nullptr
   const float* vamax;      // [B, Hkv, D] per-channel maxima of |V - mean| (per-channel V quantisation) or nullptr
+  float* qkm;              // [B, Hq, Nq] q . mean_seq(K), written by the Q blocks under smooth-K, or nullptr
 };
 
-// One 1024-thread block per (tensor, b, h, 128-row block): the tile (<= 128 x 512 x 2 B) is read from HBM
-// once and lives in registers (8 x 16 B per thread) between the amax reduction and the conversion.
-constexpr int kQuantThreads = 1024;
+// One 256-thread block per (tensor, b, h, 128-row block). The tile (<= 128 x 512 x 2 B) is read TWICE -- once for
+// the amax, once for the conversion -- instead of being parked in registers in between: the second read hits L2 (a
+// block re-reads the 64-128 KB it has just pulled in; all resident blocks together hold a few tens of MB of the
+// 126 MB L2), HBM traffic stays one read + one write per element, and without a 32-register cache several blocks fit
+// one SM, so the loads of one overlap the reduction / stores of the others. The register-cached 1024-thread version
+// (one block per SM, load -> reduce -> store strictly in sequence) ran at 2.1 TB/s = 31 % of the HBM peak at C4
+// (profiles/r02_fp8_c4_ncu.md).
+// For Q under smooth-K the block also emits qkm[row] = q_row . mean_seq(K) (the LSE correction), which used to be a
+// separate pass over Q.
+constexpr int kQuantThreads = 256;
+constexpr int kQuantUnroll = 8;   // 16-byte loads in flight per thread
 template <bool BF16>
-__global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const QuantArgs a) {
-  __shared__ float red[32];
+__global__ void __launch_bounds__(kQuantThreads, 4) quantize_e4m3_kernel(const QuantArgs a) {
+  __shared__ float red[kQuantThreads / 32];
+  __shared__ float rowdot[128];
   const int64_t blk = blockIdx.x;
   const int which = blk >= a.first_block[2] ? 2 : (blk >= a.first_block[1] ? 1 : 0);
   const int64_t local = blk - a.first_block[which];
@@ -548,13 +588,15 @@ __global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const Q
   const int r0 = tile * 128;
   const int rows = (N - r0) < 128 ? (N - r0) : 128;
   const int vec_per_row = D / 8;               // 8 elements (16 B) per vector; D % 8 == 0
-  const int nvec = rows * vec_per_row;         // <= 128 * 64 = 8 * 1024
-  // smooth-K: quantise K - mean_seq(K) (per (b, h) and channel)
+  const int nvec = rows * vec_per_row;         // <= 128 * 64
+  // smooth-K / smooth-V: quantise X - mean_seq(X) (per (b, h) and channel)
   const float* km = (which == 1 && a.ksum != nullptr) ? a.ksum + ((int64_t)b * H + h) * D
                   : (which == 2 && a.vsum != nullptr) ? a.vsum + ((int64_t)b * H + h) * D : nullptr;
   const float inv_n = 1.f / (float)N;
-  constexpr int MAXV = 8;
-  uint4 cache[MAXV];
+  // Q under smooth-K: dot of every query row with mean_seq(K) of its KV head
+  const float* qk_mean = (which == 0 && a.ksum != nullptr && a.qkm != nullptr)
+                             ? a.ksum + ((int64_t)b * a.heads[1] + h / (a.heads[0] / a.heads[1])) * D : nullptr;
+  if (qk_mean != nullptr && threadIdx.x < 128) rowdot[threadIdx.x] = 0.f;
   auto expand = [&](const uint4& raw, int c, float* f) {
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
@@ -568,18 +610,58 @@ __global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const Q
       f[4] -= k1.x * inv_n; f[5] -= k1.y * inv_n; f[6] -= k1.z * inv_n; f[7] -= k1.w * inv_n;
     }
   };
+  // vector i of the tile -> (row, 8-element column group). When the block's 256 threads cover whole rows
+  // (vec_per_row divides 256: head dims 64 / 128 / 256 / 512) a thread keeps its column and steps rows by a constant:
+  // no integer division in the loops.
+  const bool aligned = (kQuantThreads % vec_per_row) == 0;
+  const int t_r = (int)threadIdx.x / vec_per_row, t_c = (int)threadIdx.x - t_r * vec_per_row;
+  const int r_step = aligned ? kQuantThreads / vec_per_row : 0;
+  auto rc_of = [&](int i, int step, int& r, int& c) {
+    if (aligned) { r = t_r + step * r_step; c = t_c; }
+    else { r = i / vec_per_row; c = i - r * vec_per_row; }
+  };
+  auto load = [&](int r, int c) {
+    return __ldg(reinterpret_cast<const uint4*>(src + 2 * ((int64_t)(r0 + r) * rs + 8 * c)));
+  };
+  // |x| maximum of 8 packed 16-bit floats without unpacking: clear the sign bits, then compare as unsigned 16-bit
+  // integers (non-negative IEEE values order like their bit patterns); exact, so the scale equals the fp32 path's
+  auto amax_bits = [&](const uint4& raw, uint32_t acc) {
+    acc = __vmaxu2(acc, raw.x & 0x7fff7fffu); acc = __vmaxu2(acc, raw.y & 0x7fff7fffu);
+    acc = __vmaxu2(acc, raw.z & 0x7fff7fffu); acc = __vmaxu2(acc, raw.w & 0x7fff7fffu);
+    return acc;
+  };
+  // ---- pass 1: amax of the tile
   float amax = 0.f;
+  uint32_t abits = 0u;   // packed 16-bit running maxima (used when no mean is subtracted)
+  for (int i0 = threadIdx.x, st = 0; i0 < nvec; i0 += kQuantThreads * kQuantUnroll, st += kQuantUnroll) {
+    uint4 buf[kQuantUnroll];
 #pragma unroll
-  for (int v = 0; v < MAXV; ++v) {
-    const int i = threadIdx.x + v * kQuantThreads;
-    if (i < nvec) {
-      const int r = i / vec_per_row, c = i % vec_per_row;
-      cache[v] = *reinterpret_cast<const uint4*>(src + 2 * ((int64_t)(r0 + r) * rs + 8 * c));
-      float f[8];
-      expand(cache[v], c, f);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) amax = fmaxf(amax, fabsf(f[u]));
+    for (int u = 0; u < kQuantUnroll; ++u) {
+      const int i = i0 + u * kQuantThreads;
+      int r, c;
+      rc_of(i, st + u, r, c);
+      if (i < nvec) buf[u] = load(r, c);
     }
+#pragma unroll
+    for (int u = 0; u < kQuantUnroll; ++u) {
+      const int i = i0 + u * kQuantThreads;
+      if (i < nvec) {
+        if (km == nullptr) {
+          abits = amax_bits(buf[u], abits);
+        } else {
+          int r, c;
+          rc_of(i, st + u, r, c);
+          float f[8];
+          expand(buf[u], c, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(f[e]));
+        }
+      }
+    }
+  }
+  if (km == nullptr) {
+    const uint32_t m16 = max(abits & 0xffffu, abits >> 16);
+    amax = BF16 ? __uint_as_float(m16 << 16) : __half2float(__ushort_as_half((unsigned short)m16));
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
@@ -587,7 +669,7 @@ __global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const Q
   __syncthreads();
   amax = red[0];
 #pragma unroll
-  for (int i = 1; i < 32; ++i) amax = fmaxf(amax, red[i]);
+  for (int i = 1; i < kQuantThreads / 32; ++i) amax = fmaxf(amax, red[i]);
   // per-channel V: every channel has its own scale (applied in the attention epilogue), block scale = 1
   const float* cam = (which == 2 && a.vamax != nullptr) ? a.vamax + ((int64_t)b * H + h) * D : nullptr;
   // IEEE division (not the --use_fast_math reciprocal): s = amax / 448 and 1 / s are what the reference's quantiser
@@ -598,27 +680,66 @@ __global__ void __launch_bounds__(kQuantThreads, 1) quantize_e4m3_kernel(const Q
     a.scale[which][((int64_t)b * H + h) * T + tile] = scale;
     if (which == 2) atomicMax(reinterpret_cast<unsigned int*>(a.vref + (int64_t)b * H + h), __float_as_uint(scale));
   }
+  // ---- pass 2: the same vectors again (L2), converted and stored
   uint8_t* dst = a.dst[which] + (((int64_t)b * H + h) * N + r0) * dpad;
+  for (int i0 = threadIdx.x, st = 0; i0 < nvec; i0 += kQuantThreads * kQuantUnroll, st += kQuantUnroll) {
+    uint4 buf[kQuantUnroll];
 #pragma unroll
-  for (int v = 0; v < MAXV; ++v) {
-    const int i = threadIdx.x + v * kQuantThreads;
-    if (i < nvec) {
-      const int r = i / vec_per_row, c = i % vec_per_row;
-      float f[8];
-      expand(cache[v], c, f);
-      if (cam != nullptr) {
+    for (int u = 0; u < kQuantUnroll; ++u) {
+      const int i = i0 + u * kQuantThreads;
+      int r, c;
+      rc_of(i, st + u, r, c);
+      if (i < nvec) buf[u] = load(r, c);
+    }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) f[u] *= 448.f / fmaxf(__ldg(cam + 8 * c + u), 1e-12f);
+    for (int u = 0; u < kQuantUnroll; ++u) {
+      const int i = i0 + u * kQuantThreads;
+      int r, c;
+      rc_of(i, st + u, r, c);
+      float qd = 0.f;   // this vector's share of q_row . mean_seq(K)
+      if (i < nvec) {
+        float f[8];
+        expand(buf[u], c, f);
+        if (qk_mean != nullptr) {
+          const float4 k0 = __ldg(reinterpret_cast<const float4*>(qk_mean + 8 * c)), k1 = __ldg(reinterpret_cast<const float4*>(qk_mean + 8 * c + 4));
+          qd = f[0] * k0.x;
+          qd = fmaf(f[1], k0.y, qd); qd = fmaf(f[2], k0.z, qd); qd = fmaf(f[3], k0.w, qd);
+          qd = fmaf(f[4], k1.x, qd); qd = fmaf(f[5], k1.y, qd); qd = fmaf(f[6], k1.z, qd); qd = fmaf(f[7], k1.w, qd);
+        }
+        if (cam != nullptr) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] *= 448.f / fmaxf(__ldg(cam + 8 * c + e), 1e-12f);
+        }
+        const float2 inv2 = make_float2(inv, inv), z2 = make_float2(-0.f, -0.f);   // x * inv + (-0) keeps the sign of a zero product
+        const float2 g0 = ffma2(make_float2(f[0], f[1]), inv2, z2), g1 = ffma2(make_float2(f[2], f[3]), inv2, z2);
+        const float2 g2 = ffma2(make_float2(f[4], f[5]), inv2, z2), g3 = ffma2(make_float2(f[6], f[7]), inv2, z2);
+        uint2 o;
+        o.x = pack_e4m3x4(g0.x, g0.y, g1.x, g1.y);
+        o.y = pack_e4m3x4(g2.x, g2.y, g3.x, g3.y);
+        *reinterpret_cast<uint2*>(dst + (int64_t)r * dpad + 8 * c) = o;
       }
-      uint2 o;
-      o.x = pack_e4m3x4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
-      o.y = pack_e4m3x4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
-      *reinterpret_cast<uint2*>(dst + (int64_t)r * dpad + 8 * c) = o;
+      if (qk_mean != nullptr) {   // block-uniform branch: every lane takes part in the shuffles
+        if (aligned) {
+          // the lanes of a row segment (min(32, vec_per_row) consecutive lanes) hold pieces of the same row: butterfly
+          // sum inside the segment, one shared-memory add per segment (a per-lane atomicAdd on one address is a
+          // 32-way serialised CAS loop: it took more time than the HBM traffic of the whole kernel)
+          const int w = vec_per_row < 32 ? vec_per_row : 32;
+          for (int sft = w >> 1; sft > 0; sft >>= 1) qd += __shfl_xor_sync(0xffffffffu, qd, sft);
+          if (i < nvec && ((int)(threadIdx.x & 31) & (w - 1)) == 0) atomicAdd(&rowdot[r], qd);
+        } else if (i < nvec) {
+          atomicAdd(&rowdot[r], qd);
+        }
+      }
     }
   }
   if (dpad > D) {  // zero the padding bytes [D, dpad) (dpad - D is 0 or 8)
     for (int r = threadIdx.x; r < rows; r += kQuantThreads)
       *reinterpret_cast<uint2*>(dst + (int64_t)r * dpad + D) = make_uint2(0u, 0u);
+  }
+  if (qk_mean != nullptr) {
+    __syncthreads();
+    if ((int)threadIdx.x < rows)
+      a.qkm[((int64_t)b * H + h) * N + r0 + threadIdx.x] = rowdot[threadIdx.x] / (float)a.seqlen[1];
   }
 }
 
@@ -720,37 +841,11 @@ __global__ void __launch_bounds__(256) v_colamax_kernel(const void* __restrict__
   }
 }
 
-// qkm[b, h, q] = q . mean_seq(K) : one warp per query row, 16-byte loads
-template <bool BF16>
-__global__ void __launch_bounds__(256) q_dot_kmean_kernel(const void* __restrict__ q, const float* __restrict__ ksum,
-                                                          float* __restrict__ qkm, int64_t s0, int64_t s1, int64_t s2,
-                                                          int B, int Hq, int Hkv, int Nq, int Nkv, int D) {
-  const int64_t rowid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (rowid >= (int64_t)B * Hq * Nq) return;
-  const int lane = threadIdx.x & 31;
-  const int n = (int)(rowid % Nq);
-  const int h = (int)((rowid / Nq) % Hq);
-  const int b = (int)(rowid / ((int64_t)Nq * Hq));
-  const uint8_t* src = reinterpret_cast<const uint8_t*>(q) + 2 * ((int64_t)b * s0 + (int64_t)h * s1 + (int64_t)n * s2);
-  const float* km = ksum + ((int64_t)b * Hkv + h / (Hq / Hkv)) * D;
-  float acc = 0.f;
-  for (int d = lane * 8; d < D; d += 256) {
-    float f[8];
-    unpack8<BF16>(*reinterpret_cast<const uint4*>(src + 2 * d), f);
-    const float4 k0 = *reinterpret_cast<const float4*>(km + d), k1 = *reinterpret_cast<const float4*>(km + d + 4);
-    acc = fmaf(f[0], k0.x, acc); acc = fmaf(f[1], k0.y, acc); acc = fmaf(f[2], k0.z, acc); acc = fmaf(f[3], k0.w, acc);
-    acc = fmaf(f[4], k1.x, acc); acc = fmaf(f[5], k1.y, acc); acc = fmaf(f[6], k1.z, acc); acc = fmaf(f[7], k1.w, acc);
-  }
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-  if (lane == 0) qkm[rowid] = acc / (float)Nkv;
-}
-
-template <int NB, bool OUT_BF16>
-static int launch_fp8_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+template <int NB, bool OUT_BF16, int NWG>
+int launch_fp8_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                               const Fp8KernelParams& kp, int nclusters, cudaStream_t stream) {
   using Cfg = Fp8Cfg<NB>;
-  auto kern = ffpa_fwd_fp8_kernel<NB, OUT_BF16>;
+  auto kern = ffpa_fwd_fp8_kernel<NB, OUT_BF16, NWG>;
   // the opt-in shared-memory size is a per-device function attribute
   static bool attr_set[64] = {};
   int dev_id = 0;
@@ -761,7 +856,7 @@ static int launch_fp8_variant(const CUtensorMap& mq, const CUtensorMap& mk, cons
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(fp8 smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
     attr_set[dev_id] = true;
   }
-  kern<<<dim3(2 * nclusters), dim3(kThreads), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
+  kern<<<dim3(2 * nclusters), dim3((4 * NWG + 2) * 32), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "fp8 forward launch failed: %s", cudaGetErrorString(e));
   count_launch();

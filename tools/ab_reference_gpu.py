@@ -180,16 +180,12 @@ def child(argv) -> int:
     for rnd in range(2):
       for arm, (fwd, bwd) in fns.items():
         a = out["arms"][arm]
-        torch.cuda.synchronize()
-        time.sleep(1.0)   # every arm starts from the same (idle) clock / power state
         with torch.no_grad():
           for proto, tf in (("events", t_events), ("wall", t_wall)):
             ms = tf(fwd)
             key = f"fwd_ms_{proto}"
             a[key] = min(a.get(key, 1e30), ms)
         if bwd is not None:
-          torch.cuda.synchronize()
-          time.sleep(1.0)
           for proto, tf in (("events", lambda fn: t_events(fn, 2, 5)), ("wall", lambda fn: t_wall(fn, 2, 5))):
             ms = tf(bwd)
             key = f"bwd_ms_{proto}"
