@@ -97,6 +97,9 @@ void fill_fwd_sizes(ffpa_fwd_params& p, const Tensor& Q, const Tensor& K) {
 // TFLOP/s) and never more than half of (free device memory + the allocator's cached blocks). `min_workspace`
 // (CUDABackend(bwd_min_workspace=True)) or FFPA_BWD_STASH=0 asks for the O(N) plan (three recompute kernels), and an
 // allocation failure falls back to it.
+// Only consulted when a call actually has optional O(Nq*Nkv) scratch to size (callers check that first): the driver
+// query behind cudaMemGetInfo is slow and serialises with copies in flight -- calling it on every forward cost the
+// chunk-pipelined host entry its copy / compute overlap.
 uint64_t scratch_cap(const Tensor& like, const char* env_name) {
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -176,7 +179,9 @@ void ffpa_attn_forward(Tensor Q, Tensor K, Tensor V, Tensor attn_bias, Tensor O,
   Tensor ws;
   // optional O(Nq*Nkv) scratch (replay stash of head dims > 768) is bounded like the backward's: FFPA_FWD_REPLAY_MAX_GB
   // (default 2.5 GiB) and half of the free memory; chunked over heads when the whole problem does not fit
-  const uint64_t want = ffpa_b200_fwd_workspace_bytes_p(&p, scratch_cap(Q, "FFPA_FWD_REPLAY_MAX_GB"));
+  const uint64_t required = ffpa_b200_fwd_workspace_bytes_p(&p, 0);
+  uint64_t want = ffpa_b200_fwd_workspace_bytes_p(&p, ~0ull);
+  if (want > required && want > (64ull << 20)) want = ffpa_b200_fwd_workspace_bytes_p(&p, scratch_cap(Q, "FFPA_FWD_REPLAY_MAX_GB"));
   if (want > 0) {
     try {
       ws = alloc_bytes(want, Q);
@@ -232,7 +237,8 @@ void backward_impl(const Tensor& Q, const Tensor& K, const Tensor& V, const Tens
     p.d_lse = d_lse.data_ptr<float>();
   }
   const uint64_t need_min = ffpa_b200_bwd_workspace_bytes_min_p(&p);
-  uint64_t want = min_workspace ? need_min : ffpa_b200_bwd_workspace_bytes_p(&p, scratch_cap(Q, "FFPA_BWD_STASH_MAX_GB"));
+  uint64_t want = min_workspace ? need_min : ffpa_b200_bwd_workspace_bytes_p(&p, ~0ull);
+  if (want > need_min && want > (64ull << 20)) want = ffpa_b200_bwd_workspace_bytes_p(&p, scratch_cap(Q, "FFPA_BWD_STASH_MAX_GB"));
   Tensor ws;
   try {
     ws = alloc_bytes(want, Q);

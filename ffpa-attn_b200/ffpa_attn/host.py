@@ -130,21 +130,44 @@ def bind_to_gpu_numa_node(device: torch.device | str | int | None = None) -> dic
   is not exposed (then nothing is changed)."""
   import os
 
+  dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+  cpus, how, node = set(), None, None
   try:
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     props = torch.cuda.get_device_properties(dev)
     bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
     node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
-    if node < 0:
+    if node >= 0:
+      for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+      how = "sysfs"
+  except Exception:  # noqa: BLE001
+    pass
+  if not cpus:
+    # containers often hide the PCI device's numa_node (-1); NVML still knows the GPU's ideal CPU set
+    # (the "CPU Affinity" column of `nvidia-smi topo -m`)
+    try:
+      import pynvml
+
+      pynvml.nvmlInit()
+      idx = dev.index if dev.index is not None else torch.cuda.current_device()
+      visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+      if visible:
+        idx = int(visible.split(",")[idx]) if visible.split(",")[idx].isdigit() else idx
+      h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+      words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+      for w, mask in enumerate(words):
+        for bit in range(64):
+          if (int(mask) >> bit) & 1:
+            cpus.add(64 * w + bit)
+      how = "nvml"
+    except Exception:  # noqa: BLE001  (no NVML: leave the affinity alone)
       return None
-    cpus = set()
-    for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-      lo, _, hi = part.partition("-")
-      cpus.update(range(int(lo), int(hi or lo) + 1))
+  try:
     allowed = os.sched_getaffinity(0) & cpus
     if not allowed:
       return None
     os.sched_setaffinity(0, allowed)
-    return {"node": node, "cpus": len(allowed), "pci": bdf}
-  except Exception:  # noqa: BLE001  (no sysfs / no attribute: leave the affinity alone)
+    return {"via": how, "node": node, "cpus": len(allowed)}
+  except Exception:  # noqa: BLE001
     return None
