@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import torch
 
-from .functional import FFPAAttnFunc, FFPAAttnMeta
+from .functional import FFPAAttnFunc, FFPAAttnMeta, _coerce_backend
 
 
 def ffpa_attn_func(
@@ -65,15 +65,21 @@ def ffpa_attn_varlen_func(
   grid, so sequences longer than the stated maximum are a caller error. Forward and backward support every
   head dim of the dense path (8..1024).
   """
+  # flash-attn style callers pass the DEFAULTS of options this path does not implement; like the reference's
+  # _check_supported_options (/root/reference/src/ffpa_attn/cute/__init__.py:107-118) accept those and refuse
+  # anything that would change the result
+  neutral = {"window_size": (None, (None, None), (-1, -1)), "softcap": (None, 0.0, 0)}
   for name in _VARLEN_UNSUPPORTED:
-    if name in kwargs and kwargs[name] is not None:
-      raise NotImplementedError(f"ffpa_attn_varlen_func: option {name!r} is not supported")
+    val = kwargs.pop(name, None)
+    if val is None:
+      continue
+    if name in neutral and (tuple(val) if isinstance(val, (tuple, list)) else val) in neutral[name]:
+      continue
+    raise NotImplementedError(f"ffpa_attn_varlen_func: option {name}={val!r} is not supported")
   for name in ("backend", "forward_backend", "backward_backend"):
     val = kwargs.pop(name, None)
-    if val is not None and not (val == "cuda" or type(val).__name__ == "CUDABackend"):
-      raise ValueError(f"ffpa_attn_varlen_func: {name}={val!r}: the only backend of this build is 'cuda'")
-  for name in _VARLEN_UNSUPPORTED:
-    kwargs.pop(name, None)
+    if val is not None:
+      _coerce_backend(val, source=name)   # 'cuda' / CUDABackend; other strings NotImplementedError, other types TypeError
   if kwargs:
     raise TypeError(f"ffpa_attn_varlen_func() got unexpected keyword argument(s): {', '.join(sorted(kwargs))}")
   if dropout_p != 0.0:

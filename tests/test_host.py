@@ -309,8 +309,18 @@ def test_varlen_host_validation_and_no_cpu_fallback():
     ffpa_attn_varlen_func(q[None], k[None], k[None], cu, cu, 16, 16)
   with pytest.raises(TypeError, match="fp16/bf16"):
     ffpa_attn_varlen_func(q.float(), k.float(), k.float(), cu, cu, 16, 16)
-  with pytest.raises(ValueError, match="only backend"):
+  with pytest.raises(NotImplementedError, match="only backend"):   # same class as the dense entry
     ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16, backend="cutedsl")
+  with pytest.raises(TypeError):
+    ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16, backend=3)
+  # the defaults flash-attn style callers pass are accepted (reference: cute/__init__.py:107-118) ...
+  with pytest.raises(RuntimeError, match="no CPU"):
+    ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16, window_size=(None, None), softcap=0.0)
+  # ... anything that would change the result is refused
+  with pytest.raises(NotImplementedError, match="softcap"):
+    ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16, softcap=30.0)
+  with pytest.raises(NotImplementedError, match="window_size"):
+    ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16, window_size=(128, 0))
   with pytest.raises(RuntimeError, match="no CPU"):
     ffpa_attn_varlen_func(q, k, k, cu, cu, 16, 16)
 
