@@ -378,3 +378,30 @@ def test_backward_long_sequence_sampled_head():
     assert err < 1e-1 * max(1.0, want.abs().max().item()), f"{name}: {err}"
     cos = torch.nn.functional.cosine_similarity(got.float().flatten(), want.flatten(), dim=0).item()
     assert cos > 0.999, f"{name}: cosine {cos}"
+
+
+def test_bias_broadcast_over_keys_is_a_softmax_invariant():
+  """An additive bias of shape [1, 1, Nq, 1] (broadcast over KEYS, stride 0 on the last dim) shifts every score of a
+  row by the same constant: O, dQ, dK, dV must equal the unbiased run, the LSE moves by the constant, and the bias
+  gradient -- sum_k dS, reduced in the dQ kernel -- is analytically zero. Exercises the stride-0 key dim of the bias
+  in forward and backward and the in-kernel dBias reduction over keys."""
+  import ffpa_attn
+  from ffpa_attn.cuda import _ffpa_attn_forward_cuda
+
+  q, k, v, d_o = _mk(1, 2, 2, 200, 300, 128, torch.bfloat16, seed=41)
+  bias = (torch.randn(1, 1, 200, 1, generator=torch.Generator().manual_seed(3)) * 3).to(DEV).requires_grad_(True)
+  qg, kg, vg = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+  out = ffpa_attn.ffpa_attn_func(qg, kg, vg, attn_mask=bias)
+  out.backward(d_o)
+  q0, k0, v0 = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+  out0 = ffpa_attn.ffpa_attn_func(q0, k0, v0)
+  out0.backward(d_o)
+  assert (out.float() - out0.float()).abs().max().item() < 4e-3
+  for a, b_, name in ((qg.grad, q0.grad, "dQ"), (kg.grad, k0.grad, "dK"), (vg.grad, v0.grad, "dV")):
+    assert (a.float() - b_.float()).abs().max().item() < 2e-2 * max(1.0, b_.float().abs().max().item()), name
+  assert bias.grad.shape == bias.shape
+  scale_ds = float((qg.grad.float().abs().max()))
+  assert bias.grad.abs().max().item() < 2e-2 * max(1.0, scale_ds), bias.grad.abs().max().item()
+  _, lse_b = _ffpa_attn_forward_cuda(q, k, v, None, bias.detach(), 0, 1, 0, 128 ** -0.5)
+  _, lse_0 = _ffpa_attn_forward_cuda(q, k, v, None, None, 0, 1, 0, 128 ** -0.5)
+  assert (lse_b - lse_0 - bias.detach()[0, 0, :, 0][None, None]).abs().max().item() < 2e-3

@@ -301,3 +301,23 @@ def test_fp8_quantised_tiles_and_output_match_the_quantised_oracle(smooth_k):
   corr = np.corrcoef((got_o - exact).ravel(), (ref_o - exact).ravel())[0, 1]
   assert corr > 0.5, corr
   assert np.abs(lse.cpu().numpy() - exact_lse).max() < 5e-2
+
+
+def test_fp8_hybrid_is_honoured_without_causal():
+  """Explicit fp8_hybrid=True on a NON-causal call: the reference launcher runs its 16-bit stage 1 regardless of
+  causal (/root/reference/csrc/cuffpa/launch.cuh:30-58: all keys for the early rows); round 1 silently ignored it."""
+  import ffpa_attn
+
+  q, k, v = _mk(1, 2, 2, 640, 768, 256, torch.bfloat16, seed=12)
+  n0 = ffpa_attn._C.launch_count()
+  be = ffpa_attn.CUDABackend(enable_fp8=True, fp8_hybrid=True, fp8_hybrid_n_early=256)
+  out = ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=be)
+  torch.cuda.synchronize()
+  assert ffpa_attn._C.launch_count() - n0 == 1 + 3   # 16-bit stage + (K sums, quantiser, FP8 attention)
+  o16 = ffpa_attn.ffpa_attn_func(q, k, v)
+  o8 = ffpa_attn.ffpa_attn_func(q, k, v, forward_backend=ffpa_attn.CUDABackend(enable_fp8=True, fp8_hybrid=False))
+  assert (out[:, :, :256].float() - o16[:, :, :256].float()).abs().max().item() < 2e-3   # early rows: the 16-bit kernel on a row view
+  assert not torch.equal(out[:, :, 256:], o16[:, :, 256:])                  # late rows: FP8
+  assert (out[:, :, 256:].float() - o8[:, :, 256:].float()).abs().max().item() < 2e-2
+  ref, _ = orc.attention_fwd(q.cpu(), k.cpu(), v.cpu())
+  assert np.abs(out.float().cpu().numpy() - ref).max() < 4e-2

@@ -388,7 +388,7 @@ def test_unsupported_fp8_knobs_are_refused_by_name(lib):
   them (FFPA_ERR_UNSUPPORTED = -2, knob named) instead of ignoring them; so does CUDABackend."""
   from ffpa_attn import CUDABackend
 
-  base = dict(q=1, k=1, v=1, o=1, dtype=1, impl=5)
+  base = dict(q=4096, k=4096, v=4096, o=4096, dtype=1, impl=5)   # never dereferenced: the knob is refused before any launch
   for kw, word in ((dict(fp8_q_quant_method=2, fp8_k_quant_method=2), b"per_thread"), (dict(fp8_qk_mm_type=1), b"int8"),
                    (dict(fp8_pv_acc_type=0), b"f16")):
     p = capi.fwd_sizes(1, 2, 2, 256, 256, 128, **base)
