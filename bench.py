@@ -282,16 +282,20 @@ class Workload:
 
 
 def time_steps(step, n, warm):
+  """(mean, median, min) ms over n steps, one CUDA event pair per step. The secondary lines quote the MEDIAN: they run
+  back to back on a GPU that is already at its power cap, and a single slow step (clock change) moves a 5-10 step
+  mean by tens of percent."""
   for _ in range(warm):
     step()
   torch.cuda.synchronize()
-  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  a.record()
-  for _ in range(n):
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+  ev[0].record()
+  for i in range(n):
     step()
-  b.record()
+    ev[i + 1].record()
   torch.cuda.synchronize()
-  return a.elapsed_time(b) / n
+  ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
+  return ev[0].elapsed_time(ev[n]) / n, ts[n // 2], ts[0]
 
 
 def main():
@@ -517,15 +521,13 @@ def run_e2e(W, ffpa_attn, dev, world, use_dist, barrier, max_over_ranks, n_e2e):
   def e2e_step():
     ffpa_attn.ffpa_attn_host_func(hq, hk, hv, out=ho, chunks=chunks, **kw)
 
+  for _ in range(2):
+    e2e_step()
   # CPU time to ISSUE one call (no wait for the GPU): what the host side adds per step
   torch.cuda.synchronize()
   t0 = time.perf_counter()
   ffpa_attn.ffpa_attn_host_func(hq, hk, hv, out=ho, chunks=chunks, sync=False, **kw)
   issue_ms = (time.perf_counter() - t0) * 1e3
-  torch.cuda.synchronize()
-
-  for _ in range(2):
-    e2e_step()
   barrier()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
@@ -621,31 +623,32 @@ def run_also(args, dev, peaks):
     sm_clock = lambda: int(pynvml.nvmlDeviceGetClockInfo(_nv, pynvml.NVML_CLOCK_SM))  # noqa: E731
   except Exception:  # noqa: BLE001
     sm_clock = lambda: None  # noqa: E731
-  also = {"protocol": "per workload, back to back in one process: 5 warm-up steps, 10 timed steps (5 for backward kinds), CUDA "
-                      "events; sm_mhz_after = SM clock right after the timed steps (the GPU is warm: later lines run at lower "
-                      "clocks than the headline burst)"}
+  also = {"protocol": "per workload, back to back in one process: 5 warm-up steps, 10 timed steps (6 for backward kinds), one CUDA "
+                      "event pair per step; value = FLOPs / MEDIAN step time (ms_mean / ms_min alongside); sm_mhz_after = SM "
+                      "clock right after the timed steps (the GPU is warm: later lines run at lower clocks than the headline)"}
   names = [n for n in ("c2_bwd", "c3_fwd_bwd", "c3_gqa_causal_fwd_hq32hkv8n4096d512", "c4_fp8_fwd", "d320_self_fwd",
                        "d768_self_fwd", "d1024_self_fwd") if n != args.workload]
   for name in names:
     wl = WORKLOADS[name]
     try:
       W = Workload(wl, dev, 7)
-      ms = time_steps(W.step, 10 if wl["kind"] in ("fwd", "fp8_fwd") else 5, 5)
+      ms_mean, ms, ms_min = time_steps(W.step, 10 if wl["kind"] in ("fwd", "fp8_fwd") else 6, 5)
       mhz = sm_clock()
       mult = 2.0 if wl["kind"] == "fp8_fwd" else 1.0
-      rec = {"metric": METRIC[wl["kind"]], "ms_per_step": ms, "value": W.flops / ms * 1e-9, "unit": "TFLOP/s",
+      rec = {"metric": METRIC[wl["kind"]], "ms_per_step": ms, "ms_mean": ms_mean, "ms_min": ms_min,
+             "value": W.flops / ms * 1e-9, "value_best_step": W.flops / ms_min * 1e-9, "unit": "TFLOP/s",
              "peak": peaks["burst"] * mult, "frac": W.flops / ms * 1e-9 / (peaks["burst"] * mult), "sm_mhz_after": mhz}
       if name == "c2_bwd":
         # the O(N)-memory backward (three recompute kernels) next to the default (score stash from free memory)
         be = ffpa_attn.CUDABackend(bwd_min_workspace=True)
         o = ffpa_attn.ffpa_attn_func(W.qg, W.kg, W.vg, backend=be)
-        ms_r = time_steps(lambda: torch.autograd.grad(o, (W.qg, W.kg, W.vg), W.d_o, retain_graph=True), 5, 5)
+        _, ms_r, _ = time_steps(lambda: torch.autograd.grad(o, (W.qg, W.kg, W.vg), W.d_o, retain_graph=True), 6, 5)
         rec["min_workspace_ms"] = ms_r
         rec["min_workspace_value"] = W.flops / ms_r * 1e-9
         del o
       if name == "c4_fp8_fwd":
         W.kw.pop("forward_backend")
-        ms16 = time_steps(W.step, 10, 5)
+        _, ms16, _ = time_steps(W.step, 10, 5)
         rec["bf16_kernel_ms_same_inputs"] = ms16
         rec["fp8_speedup_over_bf16_kernel"] = ms16 / ms
       also[name] = rec

@@ -86,7 +86,7 @@ def child(argv) -> int:
   except Exception:  # noqa: BLE001
     sm_clock = lambda: None  # noqa: E731
 
-  res = {"package": ffpa_attn.__file__, "native": C.__file__, "protocols": {"events": "warmup 3, iters 10", "wall": "warmup 2, iters 10, one sync (reference _time_fn)"},
+  res = {"package": ffpa_attn.__file__, "native": C.__file__, "protocols": {"events": "warmup 3, iters 10, median of per-call CUDA-event times, best of 2 interleaved rounds", "wall": "warmup 2, iters 10, one sync (reference _time_fn)"},
          "cases": {}}
 
   def flops(B, H, N, D, causal):
@@ -94,16 +94,18 @@ def child(argv) -> int:
     return 4.0 * B * H * D * pairs
 
   def t_events(fn, warm=3, iters=10):
+    """median of per-call CUDA-event times (robust against a single slow call on a warm, power-capped GPU)"""
     for _ in range(warm):
       fn()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(iters):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
       fn()
-    b.record()
+      ev[i + 1].record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    return ts[iters // 2]
 
   def t_wall(fn, warm=2, iters=10):
     for _ in range(warm):
