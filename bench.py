@@ -397,6 +397,19 @@ def main():
     dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
   per_rank_ms = [round(float(x), 4) for x in per_rank.tolist()]
 
+  # ---- the reference's own protocol next to the CUDA-event number: wall clock around the public call, warm-up 2,
+  # ---- 10 iterations, ONE trailing synchronize (/root/reference/src/ffpa_attn/cli/_runner_fwd.py:84-103)
+  for _ in range(2):
+    out = step()
+  torch.cuda.synchronize()
+  tw0 = time.perf_counter()
+  for _ in range(10):
+    out = step()
+  torch.cuda.synchronize()
+  wall_ms = (time.perf_counter() - tw0) / 10 * 1e3
+  reference_protocol = {"ms_per_step": wall_ms, "value": W.flops / (wall_ms * 1e-3) * 1e-12, "unit": "TFLOP/s (this rank)",
+                        "protocol": "wall clock, warm-up 2, iters 10, one trailing synchronize (cli/_runner_fwd.py:84-103)"}
+
   # ---- sustained: the same step back to back for >= sustain_seconds (a K-step region of ~60 ms is a burst) ----
   sustained = None
   if args.sustain_seconds > 0:
@@ -490,7 +503,7 @@ def main():
     "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": (value / world / published) if published else None,
     "dtype": "fp8_e4m3" if kind == "fp8_fwd" else "bf16", "data": "synthetic", "config": config, "roofline": roofline,
-    "sustained": sustained, "per_rank_ms": per_rank_ms,
+    "sustained": sustained, "per_rank_ms": per_rank_ms, "reference_protocol": reference_protocol,
     "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
     "max_abs_err_vs_oracle": max_abs_err, "also": also,
     "reference_published": {"value": published, "unit": "TFLOP/s", "where": "bench/README.md:132 (CuTe-DSL tcgen05, B200, "
