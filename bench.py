@@ -312,9 +312,12 @@ def main():
   ap.add_argument("--sustain-seconds", type=float, default=1.0)
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-  if os.environ.get("FFPA_BENCH_WATCHDOG_S"):   # debugging aid: dump every thread's stack and exit after N seconds
+  # watchdog: a run that has not finished after 20 minutes (normal: 2-3) dumps every thread's stack and exits instead
+  # of hanging its caller (FFPA_BENCH_WATCHDOG_S overrides, 0 disables)
+  wd = float(os.environ.get("FFPA_BENCH_WATCHDOG_S", "1200"))
+  if wd > 0:
     import faulthandler
-    faulthandler.dump_traceback_later(float(os.environ["FFPA_BENCH_WATCHDOG_S"]), exit=True)
+    faulthandler.dump_traceback_later(wd, exit=True)
 
   rank = int(os.environ.get("RANK", "0"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
