@@ -76,3 +76,25 @@ def test_world_size_2_gloo_matches_unsharded(tmp_path):
   ref, _ = orc.attention_fwd(q, k, v, causal=True)
   assert np.allclose(got[:-1], ref.reshape(-1), atol=1e-12)
   assert got[-1] == 11.0  # max over ranks
+
+
+def test_bench_reference_arm_runs_on_rank_0_only():
+  """bench.py --impl reference under a multi-rank launch: rank 0 alone times the CPU route and prints the line,
+  every other rank exits 0 without work (the contract of the reference arm)."""
+  import json
+  import subprocess
+  import sys
+
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", FFPA_BENCH_WATCHDOG_S="0")
+  p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                      "--warmup", "0"], env=env, capture_output=True, text=True, timeout=300)
+  assert p.returncode == 0 and p.stdout.strip() == ""
+  env["RANK"] = env["LOCAL_RANK"] = "0"
+  p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                      "--warmup", "0", "--workload", "d320_self_fwd"], env=env, capture_output=True, text=True, timeout=300)
+  assert p.returncode == 0, p.stderr[-500:]
+  line = json.loads(p.stdout.strip().splitlines()[-1])
+  assert line["impl"] == "reference" and line["metric"] == "attn_fwd_tflops" and line["value"] > 0
+  assert line["config"]["workload"] == "d320_self_fwd" and line["cpu_baseline"]["kind"] == "port"
+  assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
