@@ -125,11 +125,16 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
 // max of the previous tile -> exp2 -> P store), and with two warps per scheduler the issue slots sat idle 59 % of the
 // time while both waited (profiles/r02_fp8_c4_ncu.md).
 template <int NB, bool OUT_BF16, int NWG>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 * NWG + 2) * 32, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 * NWG + 3) * 32, 1)
 ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const Fp8KernelParams p) {
   using Cfg = Fp8Cfg<NB>;
-  constexpr int kMmaWarp = 4 * NWG, kTmaWarp = 4 * NWG + 1;
+  // Two MMA issuers: at small head dims a KV tile is only 512 tensor-pipe cycles (12 MMA instructions), and ONE thread
+  // that waits on k_full, issues 8 QK MMAs, commits, waits on p_full / v_full, issues 4 PV MMAs and commits again could
+  // not keep up: tensor pipe 53 % busy while the softmax warps spent 24 % of all samples waiting for S
+  // (profiles/r02_fp8_c4_ncu.md). The QK issuer never blocks on the softmax of an older tile except for the S stage it
+  // is about to overwrite.
+  constexpr int kMmaWarp = 4 * NWG, kTmaWarp = 4 * NWG + 1, kPvWarp = 4 * NWG + 2;
   static_assert(NWG == 2 || NWG == 4, "softmax warpgroups: 2 or 4");
   static_assert(NWG <= Cfg::KSTG, "one S / P stage per warpgroup in flight");
   constexpr int CG = 2;
@@ -234,62 +239,73 @@ ffpa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
-    // =========================================== MMA issuer (leader CTA) ========================
+    // =========================================== QK MMA issuer (leader CTA) =====================
     if (rank == 0 && ptx::elect_one()) {
       constexpr uint32_t idesc_qk = ptx::make_idesc(0, 0, 0, 0, 128, 128);   // e4m3 x e4m3, K-major both
-      constexpr uint32_t idesc_pv = ptx::make_idesc(0, 0, 0, 1, 128, 256);   // B = V, MN-major
-      uint32_t kc = 0, vc = 0, it = 0, g = 0, gp = 0;
+      uint32_t kc = 0, it = 0, g = 0;
       for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters, ++it) {
         const int mt = item % p.n_mtiles;
         const int T = num_kv_tiles(p, mt * 128);
         ptx::mbar_wait(bar(bars.q_full), it & 1);
         ptx::tc_fence_after();
-        for (int step = 0; step < T + LA; ++step) {
-          if (step < T) {
-            const uint32_t sbuf = g % KS;
-            const uint32_t d_tmem = tmem + Cfg::S_BASE + 64 * sbuf;
-#pragma unroll
-            for (int ks = 0; ks < Cfg::KST; ++ks) {
-              const uint32_t stage = kc % Cfg::NKS, n = kc / Cfg::NKS;
-              ptx::mbar_wait(bar(bars.k_full[stage]), n & 1);
-              ptx::tc_fence_after();
-              const int nb = (NB - 2 * ks) >= 2 ? 2 : 1;
-              for (int bx = 0; bx < nb; ++bx) {
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {  // 32 e4m3 = 32 bytes per MMA K step
-                  const uint64_t ad = ptx::make_smem_desc_sw128(sQ + (2 * ks + bx) * 8192 + k4 * 32, 16, 1024);
-                  const uint64_t bd = ptx::make_smem_desc_sw128(sK + stage * 16384 + bx * 8192 + k4 * 32, 16, 1024);
-                  ptx::umma_f8_ss<CG>(d_tmem, ad, bd, idesc_qk, (ks | bx | k4) != 0 ? 1u : 0u);
-                }
-              }
-              ptx::umma_commit_mc<CG>(bar(bars.k_empty[stage]), 0x3);
-              ++kc;
-            }
-            ptx::umma_commit_mc<CG>(bar(bars.s_full[sbuf]), 0x3);
-            if (step == T - 1) ptx::umma_commit_mc<CG>(bar(bars.q_empty), 0x3);
-            ++g;
+        for (int step = 0; step < T; ++step, ++g) {
+          const uint32_t sbuf = g % KS;
+          const uint32_t d_tmem = tmem + Cfg::S_BASE + 64 * sbuf;
+          // S stage reuse: the softmax of tile g - KS has read it (and written its P) once p_full[sbuf] completed
+          if (g >= KS) {
+            ptx::mbar_wait_cluster(bar(bars.p_full[sbuf]), ((g - KS) / KS) & 1);
+            ptx::tc_fence_after();
           }
-          if (step >= LA) {
-            const uint32_t pbuf = gp % KS;
-            ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp / KS) & 1);
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KST; ++ks) {
+            const uint32_t stage = kc % Cfg::NKS, n = kc / Cfg::NKS;
+            ptx::mbar_wait(bar(bars.k_full[stage]), n & 1);
+            ptx::tc_fence_after();
+            const int nb = (NB - 2 * ks) >= 2 ? 2 : 1;
+            for (int bx = 0; bx < nb; ++bx) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {  // 32 e4m3 = 32 bytes per MMA K step
+                const uint64_t ad = ptx::make_smem_desc_sw128(sQ + (2 * ks + bx) * 8192 + k4 * 32, 16, 1024);
+                const uint64_t bd = ptx::make_smem_desc_sw128(sK + stage * 16384 + bx * 8192 + k4 * 32, 16, 1024);
+                ptx::umma_f8_ss<CG>(d_tmem, ad, bd, idesc_qk, (ks | bx | k4) != 0 ? 1u : 0u);
+              }
+            }
+            ptx::umma_commit_mc<CG>(bar(bars.k_empty[stage]), 0x3);
+            ++kc;
+          }
+          ptx::umma_commit_mc<CG>(bar(bars.s_full[sbuf]), 0x3);
+          if (step == T - 1) ptx::umma_commit_mc<CG>(bar(bars.q_empty), 0x3);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kPvWarp) {
+    // =========================================== PV MMA issuer (leader CTA) =====================
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc_pv = ptx::make_idesc(0, 0, 0, 1, 128, 256);   // B = V, MN-major
+      uint32_t vc = 0, gp = 0;
+      for (uint32_t item = cluster; item < (uint32_t)p.n_items; item += nclusters) {
+        const int mt = item % p.n_mtiles;
+        const int T = num_kv_tiles(p, mt * 128);
+        for (int step = 0; step < T; ++step, ++gp) {
+          const uint32_t pbuf = gp % KS;
+          ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp / KS) & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int s = 0; s < Cfg::NSLICE; ++s) {
+            const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
+            ptx::mbar_wait(bar(bars.v_full[stage]), n & 1);
             ptx::tc_fence_after();
 #pragma unroll
-            for (int s = 0; s < Cfg::NSLICE; ++s) {
-              const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
-              ptx::mbar_wait(bar(bars.v_full[stage]), n & 1);
-              ptx::tc_fence_after();
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {  // 32 keys per MMA: 4 atoms of 8 key-lines
-                const uint64_t ad = ptx::make_smem_desc_sw128(sP + pbuf * 8192 + kk * 32, 16, 1024);
-                const uint64_t bd = ptx::make_smem_desc_sw128(sV + stage * 16384 + kk * 4096, 16384, 1024);
-                ptx::umma_f8_ss<CG>(tmem + 128 * s, ad, bd, idesc_pv, (step > LA || kk > 0) ? 1u : 0u);
-              }
-              ptx::umma_commit_mc<CG>(bar(bars.v_empty[stage]), 0x3);
-              ++vc;
+            for (int kk = 0; kk < 4; ++kk) {  // 32 keys per MMA: 4 atoms of 8 key-lines
+              const uint64_t ad = ptx::make_smem_desc_sw128(sP + pbuf * 8192 + kk * 32, 16, 1024);
+              const uint64_t bd = ptx::make_smem_desc_sw128(sV + stage * 16384 + kk * 4096, 16384, 1024);
+              ptx::umma_f8_ss<CG>(tmem + 128 * s, ad, bd, idesc_pv, (step > 0 || kk > 0) ? 1u : 0u);
             }
-            ptx::umma_commit_mc<CG>(bar(bars.p_empty[pbuf]), 0x3);
-            ++gp;
+            ptx::umma_commit_mc<CG>(bar(bars.v_empty[stage]), 0x3);
+            ++vc;
           }
+          ptx::umma_commit_mc<CG>(bar(bars.p_empty[pbuf]), 0x3);
         }
       }
     }
@@ -856,7 +872,7 @@ int launch_fp8_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(fp8 smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
     attr_set[dev_id] = true;
   }
-  kern<<<dim3(2 * nclusters), dim3((4 * NWG + 2) * 32), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
+  kern<<<dim3(2 * nclusters), dim3((4 * NWG + 3) * 32), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "fp8 forward launch failed: %s", cudaGetErrorString(e));
   count_launch();
