@@ -10,11 +10,11 @@ namespace ffpa {
 
 template <bool BF16>
 int dispatch_fwd_dtype(int nqk, int mode, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                       const CUtensorMap& msp, const FwdKernelParams& kp, int nclusters, cudaStream_t stream);
+                       const CUtensorMap& msp, const CUtensorMap& mo, const FwdKernelParams& kp, int nclusters, cudaStream_t stream);
 extern template int dispatch_fwd_dtype<true>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                                             const CUtensorMap&, const FwdKernelParams&, int, cudaStream_t);
+                                             const CUtensorMap&, const CUtensorMap&, const FwdKernelParams&, int, cudaStream_t);
 extern template int dispatch_fwd_dtype<false>(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                                              const CUtensorMap&, const FwdKernelParams&, int, cudaStream_t);
+                                              const CUtensorMap&, const CUtensorMap&, const FwdKernelParams&, int, cudaStream_t);
 namespace replay {
 template <bool BF16>
 int launch_fwd_replay(const CUtensorMap& map_p, const CUtensorMap& map_v, const FwdReplayParams& kp, int nclusters,
@@ -120,6 +120,10 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
     return set_error(FFPA_ERR_CUDA, "cuTensorMapEncodeTiled failed (strides must be multiples of 8 elements, base 16-byte aligned)");
 
   FwdKernelParams kp{};
+  // O store map: [64 head dims x 32 rows] boxes, one per softmax warp and slice (epilogue of the forward kernel).
+  // Optional: an O the tensor-map encoder refuses is written with per-thread stores instead.
+  CUtensorMap mo = mq;
+  kp.o_tma = make_map(&mo, a.o, a.o_stride, mb, a.heads_q, mnq, D, 64, 32) ? 1 : 0;
   kp.o = a.o;
   kp.lse = a.lse;
   kp.lse_bh_stride = a.lse_bh_stride > 0 ? a.lse_bh_stride : a.seqlen_q;
@@ -217,8 +221,8 @@ int launch_fwd_sm100(const ffpa_fwd_params& a, cudaStream_t stream) {
   int mode = 0;  // fast
   if (a.dropout_p > 0.f) mode = 2;
   else if (a.bias_kind != FFPA_BIAS_NONE || !(a.softmax_scale > 0.f)) mode = 1;
-  int rc = (a.dtype == FFPA_DTYPE_BF16) ? dispatch_fwd_dtype<true>(nqk, mode, mq, mk, mv, msp, kp, nclusters, stream)
-                                        : dispatch_fwd_dtype<false>(nqk, mode, mq, mk, mv, msp, kp, nclusters, stream);
+  int rc = (a.dtype == FFPA_DTYPE_BF16) ? dispatch_fwd_dtype<true>(nqk, mode, mq, mk, mv, msp, mo, kp, nclusters, stream)
+                                        : dispatch_fwd_dtype<false>(nqk, mode, mq, mk, mv, msp, mo, kp, nclusters, stream);
   if (rc) return rc;
   if (use_replay) {
     FwdReplayParams gp{};

@@ -208,7 +208,7 @@ template <int NQK, bool BF16, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FwdCfg<NQK>::THREADS, 1)
 ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_sp,
-                const FwdKernelParams p) {
+                const __grid_constant__ CUtensorMap map_o, const FwdKernelParams p) {
   using Cfg = FwdCfg<NQK>;
   constexpr int CG = 2;
   constexpr uint32_t KS = Cfg::KSTG;   // S/P pipeline depth
@@ -255,6 +255,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     ptx::prefetch_tmap(&map_q);
     ptx::prefetch_tmap(&map_k);
     ptx::prefetch_tmap(&map_v);
+    if (p.o_tma) ptx::prefetch_tmap(&map_o);
   }
   if (warp == kMmaWarp) {
     ptx::tmem_alloc<CG>(ptx::smem_u32(&tmem_slot), 512);
@@ -485,6 +486,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint32_t g = 0;                      // global tile counter at the start of the item (ALT) / running (column split)
     uint32_t uw = 0;                     // ALT: tiles processed by this warpgroup
     uint32_t pub[4] = {0, 0, 0, 0};      // ALT: completed publications of m_full[0..3]
+    bool epi_pending = false;            // a bulk store of the last epilogue may still be reading the P ring
     for (uint32_t kidx = 0;; ++kidx) {
       const int item_s = next_item(p, cluster, nclusters, kidx);
       if (item_s < 0) break;
@@ -573,6 +575,12 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         float tmax = fmaxf(fmax3(mx0, mx1, mx2), mx3);
         xch[xb][slot][row] = tmax;
+        if (epi_pending) {
+          // O tiles of the previous item were staged in the P ring (epilogue): their bulk stores must have read them
+          // before any warp that meets this one at the barrier below writes P
+          if (ptx::lane_id() == 0) ptx::bulk_wait_group_read0();
+          epi_pending = false;
+        }
         if constexpr (ALT) {
           ptx::named_bar_sync(1 + 2 * wgi + rgrp, 64);      // the two lane halves of this warpgroup's rows
           tmax = fmaxf(tmax, xch[xb][slot ^ 1][row]);
@@ -747,6 +755,26 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           p.stash_inv[(int64_t)bh * p.n_mt_even * 128 + gq] = inv;
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
                         2 * ((int64_t)fi.bt * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)(fi.qoff + gq) * p.o_stride[2]);
+        const bool o_al32 = (reinterpret_cast<uintptr_t>(orow) & 31u) == 0;   // 32-byte stores need it (strides are only 16-byte granular)
+        // TMA-store path. In the direct path every lane writes another row, so each store instruction costs 32 LSU
+        // wavefronts and the epilogue of a 128 x 512 tile keeps the LSU busy for ~4000 cycles -- longer than the QK MMA
+        // of the next item's first tile that should hide it (profiles/r02_fwd_epilogue.md). Here a warp stages its
+        // 32 rows x 64 head dims (4 KB, 128-byte swizzle) in a piece of the P ring and one lane issues a bulk store.
+        // The P ring is idle: every PV of this item has retired (p_empty above), and the next writers of the piece a
+        // warp borrows are warps that meet this one at a named barrier (row-max exchange) before they write P.
+        //   column-split mode: piece (stage j/2, key half j%2, row group) with j = 2 * warpgroup + lane half
+        //   alternate-tile mode: a stage of the parity this warpgroup itself writes next
+        // Packed mode: rows past the end of a sequence belong to the next one, so partial row blocks go direct.
+        constexpr bool kTmaEpi = (CPT != 16) && Cfg::NSW == 8;
+        const int r0 = q0 + 64 * (int)rank + 32 * (int)rgrp;   // first row of this warp inside its sequence
+        const bool use_tma = kTmaEpi && p.o_tma != 0 && p.kv_splits == 1 && (p.cu_q == nullptr || r0 + 32 <= seq_q);
+        const uint32_t epi_j = ALT ? (((g + wgi) & 1u) * 2u + kh) : (wgi * 2u + kh);
+        const uint32_t epi_base = sP + (epi_j >> 1) * 16384u + (epi_j & 1u) * 8192u + rgrp * 4096u;
+        if (Cfg::NPASS == 2 && p.stash_p != nullptr && use_tma) {
+          // replay path: the store warp may still be draining the last P tiles of this item out of the ring
+#pragma unroll
+          for (uint32_t st = 0; st < KS; ++st) ptx::mbar_wait(bar(bars.p_stored[(g + st) % KS]), (((g + st) / KS) & 1) ^ 1);
+        }
 #pragma unroll
         for (int s = 0; s < Cfg::NSLICE; ++s) {
           if (256 * s >= dvw) break;
@@ -755,6 +783,44 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           constexpr int EC = CPT == 16 ? 16 : 32;     // columns per TMEM load
           const uint32_t eg = ALT ? wgi : ch;
           const int part = ns / 2 / EG;  // columns of this slice handled by each warpgroup
+          if constexpr (kTmaEpi) {
+            if (use_tma && part == 64) {
+              const int dbox = dv0 + 256 * s + 128 * (int)kh + 64 * (int)eg;
+              if (dbox >= p.head_dim) continue;   // padding columns only
+              const uint32_t srow = epi_base + (row & 31u) * 128u;
+              uint32_t w[32];   // 64 head dims of this row, packed
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t orr[32];
+                ptx::tmem_ld_x32(tmem + lane_base + 128 * s + 64 * (int)eg + 32 * hh, orr);
+                ptx::tmem_wait_ld();
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                  const float a = __uint_as_float(orr[2 * u]) * inv, c = __uint_as_float(orr[2 * u + 1]) * inv;
+                  w[16 * hh + u] = BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
+                }
+              }
+              // the piece may still be read by the store of the previous slice / item: that wait overlaps the TMEM
+              // loads and packing above
+              if (ptx::lane_id() == 0) ptx::bulk_wait_group_read0();
+              __syncwarp();
+#pragma unroll
+              for (int v = 0; v < 8; ++v) {
+                const uint32_t addr = srow + (((uint32_t)v ^ (row & 7u)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * v]), "r"(w[4 * v + 1]), "r"(w[4 * v + 2]),
+                             "r"(w[4 * v + 3])
+                             : "memory");
+              }
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (ptx::lane_id() == 0) {
+                ptx::tma_store_4d(&map_o, epi_base, dbox, fi.qoff + r0, h, fi.bt);
+                ptx::bulk_commit_group();
+              }
+              epi_pending = true;   // the piece goes back to the P ring: waited for before the next P tile is written
+              continue;
+            }
+          }
 #pragma unroll 1
           for (int c0 = (int)eg * part; c0 < (int)(eg + 1) * part; c0 += EC) {
             uint32_t orr[EC];
@@ -763,28 +829,40 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             ptx::tmem_wait_ld();
             const int d0 = dv0 + 256 * s + (ns / 2) * (int)kh + c0;
             if (row_ok) {
+              if (p.kv_splits > 1) {
+                // fp32 partial of this KV split, normalised by its own row sum
+                float* po = p.part_o + ((((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq) * (int64_t)p.head_dim;
 #pragma unroll
-              for (int v = 0; v < EC / 8; ++v) {
-                const int d = d0 + 8 * v;
-                if (d < p.head_dim) {
-                  if (p.kv_splits > 1) {
-                    // fp32 partial of this KV split, normalised by its own row sum
-                    float* po = p.part_o + ((((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq) * (int64_t)p.head_dim + d;
-                    *reinterpret_cast<float4*>(po) = make_float4(__uint_as_float(orr[8 * v]) * inv, __uint_as_float(orr[8 * v + 1]) * inv,
-                                                                 __uint_as_float(orr[8 * v + 2]) * inv, __uint_as_float(orr[8 * v + 3]) * inv);
-                    *reinterpret_cast<float4*>(po + 4) = make_float4(__uint_as_float(orr[8 * v + 4]) * inv, __uint_as_float(orr[8 * v + 5]) * inv,
-                                                                     __uint_as_float(orr[8 * v + 6]) * inv, __uint_as_float(orr[8 * v + 7]) * inv);
-                    continue;
-                  }
-                  uint32_t w[4];
+                for (int v = 0; v < EC / 4; ++v)
+                  if (d0 + 4 * v < p.head_dim)
+                    *reinterpret_cast<float4*>(po + d0 + 4 * v) =
+                        make_float4(__uint_as_float(orr[4 * v]) * inv, __uint_as_float(orr[4 * v + 1]) * inv,
+                                    __uint_as_float(orr[4 * v + 2]) * inv, __uint_as_float(orr[4 * v + 3]) * inv);
+              } else {
+                uint32_t w[EC / 2];
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const float a = __uint_as_float(orr[8 * v + 2 * u]) * inv;
-                    const float c = __uint_as_float(orr[8 * v + 2 * u + 1]) * inv;
-                    w[u] = BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
-                  }
-                  *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int u = 0; u < EC / 2; ++u) {
+                  const float a = __uint_as_float(orr[2 * u]) * inv, c = __uint_as_float(orr[2 * u + 1]) * inv;
+                  w[u] = BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
                 }
+#ifndef FFPA_DBG_SKIP_O_STORE
+#pragma unroll
+                for (int v = 0; v < EC / 16; ++v) {
+                  const int d = d0 + 16 * v;
+                  // every lane writes another row, so a store instruction costs one LSU wavefront per lane whatever its
+                  // width: one 32-byte store (a whole sector) per 16 head dims where the row allows it, else two of 16
+                  if (o_al32 && d + 16 <= p.head_dim) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + 2 * d), "r"(w[8 * v]),
+                                 "r"(w[8 * v + 1]), "r"(w[8 * v + 2]), "r"(w[8 * v + 3]), "r"(w[8 * v + 4]), "r"(w[8 * v + 5]),
+                                 "r"(w[8 * v + 6]), "r"(w[8 * v + 7])
+                                 : "memory");
+                  } else {
+                    if (d < p.head_dim) *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(w[8 * v], w[8 * v + 1], w[8 * v + 2], w[8 * v + 3]);
+                    if (d + 8 < p.head_dim)
+                      *reinterpret_cast<uint4*>(orow + 2 * d + 16) = make_uint4(w[8 * v + 4], w[8 * v + 5], w[8 * v + 6], w[8 * v + 7]);
+                  }
+                }
+#endif
               }
             }
           }
@@ -801,6 +879,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   }
 
+  if (warp < (uint32_t)kSoftmaxWarps && ptx::lane_id() == 0) ptx::bulk_wait_group0();   // O tiles stored by the epilogue
   ptx::tc_fence_before();
   ptx::cluster_sync();
   if (warp == kMmaWarp) ptx::tmem_dealloc<CG>(tmem, 512);
@@ -863,7 +942,7 @@ int launch_merge_splits(const float* part_o, const float* part_lse, void* o, flo
 // host launcher pieces (instantiated per dtype in ffpa_fwd_bf16.cu / ffpa_fwd_f16.cu)
 // ------------------------------------------------------------------------------------------------
 template <int NQK, bool BF16, int MODE>
-static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& msp,
+static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& msp, const CUtensorMap& mo,
                           const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
   using Cfg = FwdCfg<NQK>;
   auto kern = ffpa_fwd_kernel<NQK, BF16, MODE>;
@@ -877,7 +956,7 @@ static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CU
     if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_DYN, cudaGetErrorString(e));
     attr_set[dev_id] = true;
   }
-  kern<<<dim3(2 * nclusters), dim3(Cfg::THREADS), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, msp, kp);
+  kern<<<dim3(2 * nclusters), dim3(Cfg::THREADS), Cfg::SMEM_DYN, stream>>>(mq, mk, mv, msp, mo, kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFPA_ERR_CUDA, "forward launch failed: %s", cudaGetErrorString(e));
   count_launch();
@@ -885,35 +964,35 @@ static int launch_variant(const CUtensorMap& mq, const CUtensorMap& mk, const CU
 }
 
 template <bool BF16, int MODE>
-static int dispatch_nqk(int nqk, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& msp,
+static int dispatch_nqk(int nqk, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& msp, const CUtensorMap& mo,
                         const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
   switch (nqk) {
-    case 1: return launch_variant<1, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 2: return launch_variant<2, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 3: return launch_variant<3, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 4: return launch_variant<4, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 5: return launch_variant<5, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 6: return launch_variant<6, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 7: return launch_variant<7, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 8: return launch_variant<8, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 9: return launch_variant<9, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 10: return launch_variant<10, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 11: return launch_variant<11, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 12: return launch_variant<12, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 13: return launch_variant<13, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 14: return launch_variant<14, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 15: return launch_variant<15, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
-    case 16: return launch_variant<16, BF16, MODE>(mq, mk, mv, msp, kp, nclusters, stream);
+    case 1: return launch_variant<1, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 2: return launch_variant<2, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 3: return launch_variant<3, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 4: return launch_variant<4, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 5: return launch_variant<5, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 6: return launch_variant<6, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 7: return launch_variant<7, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 8: return launch_variant<8, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 9: return launch_variant<9, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 10: return launch_variant<10, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 11: return launch_variant<11, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 12: return launch_variant<12, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 13: return launch_variant<13, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 14: return launch_variant<14, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 15: return launch_variant<15, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
+    case 16: return launch_variant<16, BF16, MODE>(mq, mk, mv, msp, mo, kp, nclusters, stream);
     default: return set_error(FFPA_ERR_UNSUPPORTED, "head_dim > 1024 not supported");
   }
 }
 
 template <bool BF16>
-int dispatch_fwd_dtype(int nqk, int mode, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& msp,
+int dispatch_fwd_dtype(int nqk, int mode, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& msp, const CUtensorMap& mo,
                        const FwdKernelParams& kp, int nclusters, cudaStream_t stream) {
-  if (mode == kModeFast) return dispatch_nqk<BF16, kModeFast>(nqk, mq, mk, mv, msp, kp, nclusters, stream);
-  if (mode == kModeGeneral) return dispatch_nqk<BF16, kModeGeneral>(nqk, mq, mk, mv, msp, kp, nclusters, stream);
-  return dispatch_nqk<BF16, kModeDropout>(nqk, mq, mk, mv, msp, kp, nclusters, stream);
+  if (mode == kModeFast) return dispatch_nqk<BF16, kModeFast>(nqk, mq, mk, mv, msp, mo, kp, nclusters, stream);
+  if (mode == kModeGeneral) return dispatch_nqk<BF16, kModeGeneral>(nqk, mq, mk, mv, msp, mo, kp, nclusters, stream);
+  return dispatch_nqk<BF16, kModeDropout>(nqk, mq, mk, mv, msp, mo, kp, nclusters, stream);
 }
 
 }  // namespace ffpa

@@ -40,6 +40,7 @@ struct FwdKernelParams {
   float* stash_f;    // [B Hq][q tiles (even)][KV tiles][128]
   float* stash_inv;  // [B Hq][q tiles (even) * 128]
   int nk_pad, n_mt_even, n_pass;
+  int o_tma;   // map_o is valid: the epilogue may TMA-store O tiles staged in the (then idle) P buffers
 };
 
 // second-slab forward GEMM over stashed P tiles (256 query rows per 2-CTA cluster, M = 256)
