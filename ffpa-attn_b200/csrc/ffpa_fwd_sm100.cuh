@@ -74,7 +74,8 @@ struct FwdCfg {
   static constexpr int MMA_WARP = NSW, TMA_WARP = NSW + 1;
   // two-slab head dims carry one more warp: it TMA-stores the P tiles for the replay path (see FwdKernelParams)
   static constexpr int STORE_WARP = NSW + 2;
-  static constexpr int THREADS = (NSW + 2 + (DVP > 768 ? 1 : 0)) * 32;
+  static constexpr int V_WARP = NSW + 2;   // separate-ring head dims (<= 512): a second TMA producer warp streams V
+  static constexpr int THREADS = (NSW + 2 + ((DVP > 768 || HD <= FFPA_UNIFIED_MIN_HD) ? 1 : 0)) * 32;
   static constexpr int P_BYTES = KSTG * 16384;
   // Wide heads keep Q resident (96-128 KB), leaving too little for separate K and V rings; they use
   // ONE ring of 16 KB stages shared by K stages and V slices (a slice = 2 consecutive stages), so
@@ -204,6 +205,21 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
+#ifdef FFPA_TRACE
+// development aid (never built into the shipped library): per-cluster, per-item clock64 stamps of the pipeline roles
+__device__ unsigned long long* g_fwd_trace = nullptr;
+#ifdef FFPA_TRACE_SETTER
+extern "C" void ffpa_dbg_set_fwd_trace(unsigned long long* ptr) { cudaMemcpyToSymbol(g_fwd_trace, &ptr, sizeof(ptr)); }
+#endif
+#define FFPA_STAMP(kidx_, ev_)                                                                              \
+  do {                                                                                                      \
+    if (g_fwd_trace != nullptr && rank == 0 && (kidx_) < 64)                                                \
+      g_fwd_trace[((size_t)cluster * 64 + (kidx_)) * 16 + (ev_)] = (unsigned long long)clock64();            \
+  } while (0)
+#else
+#define FFPA_STAMP(kidx_, ev_) do {} while (0)
+#endif
+
 template <int NQK, bool BF16, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FwdCfg<NQK>::THREADS, 1)
 ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -269,28 +285,39 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int group = p.heads_q / p.heads_kv;
 
   if (warp == kTmaWarp) {
-    // =========================================== TMA producer ===================================
+    // =========================================== TMA producer: Q and K (and V on the shared ring) ===========
+    // Separate rings (head dims <= 512): this thread streams Q and K only and the V warp below streams V, so neither
+    // stream ever queues behind a ring slot of the other. With ONE thread doing both, the next item's Q and first K
+    // tile were requested only after the last V tile of the current item had found a free slot (= after its
+    // second-to-last PV MMA), and every item started with ~3000 idle tensor-pipe cycles (profiles/r02_fwd_epilogue.md).
+    // Shared ring (wider heads): the stream order is fixed by the ring, but the next item's Q is requested before the
+    // last V tile, whose slot cannot free before Q's own (q_empty fires when the last QK MMA completes).
     if (ptx::elect_one()) {
-      uint32_t kc = 0, vc = 0, it = 0;
+      uint32_t kc = 0, it = 0;
+      bool q_ahead = false;
       const uint32_t l_q_full = ptx::mapa(bar(bars.q_full), 0);
+      auto load_q = [&](const FwdItem& f, uint32_t itn) {
+        ptx::mbar_wait(bar(bars.q_empty), (itn & 1) ^ 1);
+        if (rank == 0) ptx::mbar_expect_tx(bar(bars.q_full), 2 * Cfg::Q_BYTES);
+#pragma unroll
+        for (int jb = 0; jb < NQK; ++jb)
+          ptx::tma_load_4d_2sm(sQ + jb * 8192, &map_q, l_q_full, jb * 64, f.qoff + f.mt * 128 + 64 * (int)rank, f.bh % p.heads_q, f.bt);
+      };
       for (uint32_t kidx = 0;; ++kidx, ++it) {
         const int item_s = next_item(p, cluster, nclusters, kidx);
         if (item_s < 0) break;
         const uint32_t item = (uint32_t)item_s;
         const FwdItem fi = decode_fwd_item<Cfg::NPASS>(p, item);
-        const int mt = fi.mt, pass = fi.pass, bh = fi.bh;
+        const int pass = fi.pass, bh = fi.bh;
         const int h = bh % p.heads_q, b = fi.bt;   // b: batch coordinate of the tensor maps
         const int hk = h / group;
-        const int q0 = fi.qoff + mt * 128;         // token rows (packed mode: offset of the sequence)
         const int T = fi.T, tbeg = fi.tbeg;
         if (T <= 0) { --it; continue; }   // empty KV split: no barrier traffic (the for-increment re-adds 1)
         const int dv0 = pass * Cfg::DSLAB, dvw = Cfg::slab_w(pass);
-        ptx::mbar_wait(bar(bars.q_empty), (it & 1) ^ 1);
-        if (rank == 0) ptx::mbar_expect_tx(bar(bars.q_full), 2 * Cfg::Q_BYTES);
-#pragma unroll
-        for (int jb = 0; jb < NQK; ++jb)
-          ptx::tma_load_4d_2sm(sQ + jb * 8192, &map_q, l_q_full, jb * 64, q0 + 64 * (int)rank, h, b);
-        for (int step = 0; step < T + LA; ++step) {
+        if (q_ahead) q_ahead = false;
+        else load_q(fi, it);
+        FFPA_STAMP(kidx, 7);
+        for (int step = 0; step < T + (Cfg::UNIFIED ? LA : 0); ++step) {
           if (step < T) {
             const int kv0 = fi.koff + (tbeg + step) * 128;
 #pragma unroll
@@ -312,12 +339,24 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               ++kc;
             }
           }
-          if (step >= LA) {
-            const int kv0 = fi.koff + (tbeg + step - LA) * 128;
+          if constexpr (Cfg::UNIFIED) {
+            if (step == T) {
+              // first drain step: request the next non-empty item's Q before the last V tiles
+              for (uint32_t kn = kidx + 1;; ++kn) {
+                const int nx = next_item(p, cluster, nclusters, kn);
+                if (nx < 0) break;
+                const FwdItem fn = decode_fwd_item<Cfg::NPASS>(p, (uint32_t)nx);
+                if (fn.T <= 0) continue;
+                load_q(fn, it + 1);
+                q_ahead = true;
+                break;
+              }
+            }
+            if (step >= LA) {
+              const int kv0 = fi.koff + (tbeg + step - LA) * 128;
 #pragma unroll
-            for (int s = 0; s < Cfg::NSLICE; ++s) {
-              if (256 * s >= dvw) break;
-              if constexpr (Cfg::UNIFIED) {
+              for (int s = 0; s < Cfg::NSLICE; ++s) {
+                if (256 * s >= dvw) break;
                 // slice = stages (st, st+1) of the shared ring; kc is the shared counter
                 const uint32_t st = kc % Cfg::NKS, n = kc / Cfg::NKS;
                 const int nsu = Cfg::slice_n(dvw, s);
@@ -332,19 +371,39 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                   }
                 }
                 kc += 2;
-                continue;
               }
-              const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
-              ptx::mbar_wait(bar(bars.v_empty[stage]), (n & 1) ^ 1);
-              const int ns = Cfg::slice_n(dvw, s);
-              const int nb = ns / 128;  // 64-wide boxes this CTA loads
-              if (rank == 0) ptx::mbar_expect_tx(bar(bars.v_full[stage]), 2 * nb * 16384);
-              const uint32_t l_full = ptx::mapa(bar(bars.v_full[stage]), 0);
-              for (int bx = 0; bx < nb; ++bx)
-                ptx::tma_load_4d_2sm(sV + stage * 32768 + bx * 16384, &map_v, l_full,
-                                     dv0 + 256 * s + (ns / 2) * (int)rank + 64 * bx, kv0, hk, b);
-              ++vc;
             }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (!Cfg::UNIFIED && warp == Cfg::V_WARP) {
+    // =========================================== TMA producer: V (separate rings) ===========================
+    if (ptx::elect_one()) {
+      uint32_t vc = 0;
+      for (uint32_t kidx = 0;; ++kidx) {
+        const int item_s = next_item(p, cluster, nclusters, kidx);
+        if (item_s < 0) break;
+        const FwdItem fi = decode_fwd_item<Cfg::NPASS>(p, (uint32_t)item_s);
+        if (fi.T <= 0) continue;
+        const int hk = (fi.bh % p.heads_q) / group, b = fi.bt;
+        const int dv0 = fi.pass * Cfg::DSLAB, dvw = Cfg::slab_w(fi.pass);
+        for (int step = 0; step < fi.T; ++step) {
+          const int kv0 = fi.koff + (fi.tbeg + step) * 128;
+#pragma unroll
+          for (int s = 0; s < Cfg::NSLICE; ++s) {
+            if (256 * s >= dvw) break;
+            const uint32_t stage = vc % Cfg::NVS, n = vc / Cfg::NVS;
+            ptx::mbar_wait(bar(bars.v_empty[stage]), (n & 1) ^ 1);
+            const int ns = Cfg::slice_n(dvw, s);
+            const int nb = ns / 128;  // 64-wide boxes this CTA loads
+            if (rank == 0) ptx::mbar_expect_tx(bar(bars.v_full[stage]), 2 * nb * 16384);
+            const uint32_t l_full = ptx::mapa(bar(bars.v_full[stage]), 0);
+            for (int bx = 0; bx < nb; ++bx)
+              ptx::tma_load_4d_2sm(sV + stage * 32768 + bx * 16384, &map_v, l_full,
+                                   dv0 + 256 * s + (ns / 2) * (int)rank + 64 * bx, kv0, hk, b);
+            ++vc;
           }
         }
       }
@@ -366,6 +425,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (T <= 0) { --it; continue; }
         ptx::mbar_wait(bar(bars.q_full), it & 1);
         ptx::tc_fence_after();
+        FFPA_STAMP(kidx, 0);
         for (int step = 0; step < T + LA; ++step) {
           if (step < T) {
             const uint32_t sbuf = g % KS;
@@ -401,6 +461,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const uint32_t pbuf = gp % KS;
             ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp / KS) & 1);
             ptx::tc_fence_after();
+            if (step == LA) FFPA_STAMP(kidx, 1);
+            if (step == T + LA - 1) FFPA_STAMP(kidx, 2);
 #pragma unroll
             for (int s = 0; s < Cfg::NSLICE; ++s) {
               if (256 * s >= dvw) break;
@@ -487,11 +549,15 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint32_t uw = 0;                     // ALT: tiles processed by this warpgroup
     uint32_t pub[4] = {0, 0, 0, 0};      // ALT: completed publications of m_full[0..3]
     bool epi_pending = false;            // a bulk store of the last epilogue may still be reading the P ring
+    // the next item is looked up and decoded (schedule-table load, integer divisions: ~1000 cycles) while this item's
+    // last PV MMA drains, not between the epilogue and the first softmax of the next item where nothing hides it
+    int ahead_s = next_item(p, cluster, nclusters, 0);
+    FwdItem ahead_fi{};
+    if (ahead_s >= 0) ahead_fi = decode_fwd_item<Cfg::NPASS>(p, (uint32_t)ahead_s);
     for (uint32_t kidx = 0;; ++kidx) {
-      const int item_s = next_item(p, cluster, nclusters, kidx);
+      const int item_s = ahead_s;
       if (item_s < 0) break;
-      const uint32_t item = (uint32_t)item_s;
-      const FwdItem fi = decode_fwd_item<Cfg::NPASS>(p, item);
+      const FwdItem fi = ahead_fi;
       const int mt = fi.mt, pass = fi.pass, bh = fi.bh;
       const int h = bh % p.heads_q, b = bh / p.heads_q;
       const int q0 = mt * 128;
@@ -505,6 +571,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // empty KV split (causal rows that end before this split starts): contributes nothing
         if (p.part_lse != nullptr && wgi == 0 && kh == 0 && gq < seq_q)
           p.part_lse[(((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq] = NEG_INF;
+        ahead_s = next_item(p, cluster, nclusters, kidx + 1);
+        if (ahead_s >= 0) ahead_fi = decode_fwd_item<Cfg::NPASS>(p, (uint32_t)ahead_s);
         continue;
       }
 
@@ -514,6 +582,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t xb = ALT ? (uw & 1) : (gi & 1);   // row-max exchange buffer
         ptx::mbar_wait(bar(bars.s_full[sbuf]), (gi / KS) & 1);
         ptx::tc_fence_after();
+        if (t == 0 && i == 0) FFPA_STAMP(kidx, 3);
         uint32_t sr[CPT];
         if constexpr (CPT == 64) {
           ptx::tmem_ld_x32(tmem + lane_base + Cfg::S_BASE + 64 * sbuf, sr);
@@ -688,8 +757,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           // O may only be touched once PV of tile g-1 has retired; each warpgroup scales half the columns
           ptx::mbar_wait(bar(bars.p_empty[(gi - 1) % KS]), ((gi - 1) / KS) & 1);
           ptx::tc_fence_after();
-#pragma unroll 1
           constexpr int RC = CPT == 16 ? 16 : 32;   // columns per TMEM round trip
+#pragma unroll 1
           for (int c0 = (int)ch * (dvw / 2 / CQ); c0 < (int)(ch + 1) * (dvw / 2 / CQ); c0 += RC) {
             uint32_t orr[RC];
             if constexpr (RC == 32) ptx::tmem_ld_x32(tmem + lane_base + c0, orr);
@@ -705,6 +774,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
+        if (t == 0 && i == 0) FFPA_STAMP(kidx, 4);
         if (ptx::lane_id() == 0) {
           ptx::mbar_arrive_cluster(l_p_full0 + 8u * sbuf);  // p_full[] is contiguous
           if (stash) ptx::mbar_arrive(bar(bars.p_written[sbuf]));
@@ -713,6 +783,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
 
       // ---------------- epilogue: O / l -> global, LSE ----------------
+      ahead_s = next_item(p, cluster, nclusters, kidx + 1);
+      if (ahead_s >= 0) ahead_fi = decode_fwd_item<Cfg::NPASS>(p, (uint32_t)ahead_s);
       {
         float l_tot;
         uint32_t gl;
@@ -749,6 +821,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         l_tot = (xl[0][row] + xl[1][row]) + (xl[2][row] + xl[3][row]);
         if constexpr (CQ == 4) l_tot += (xl[4][row] + xl[5][row]) + (xl[6][row] + xl[7][row]);
         }
+        if (t == 0) FFPA_STAMP(kidx, 5);
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
         const bool row_ok = gq < seq_q;
         if (Cfg::NPASS == 2 && p.stash_p != nullptr && wgi == 0 && kh == 0)
@@ -789,21 +862,26 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               if (dbox >= p.head_dim) continue;   // padding columns only
               const uint32_t srow = epi_base + (row & 31u) * 128u;
               uint32_t w[32];   // 64 head dims of this row, packed
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                uint32_t orr[32];
-                ptx::tmem_ld_x32(tmem + lane_base + 128 * s + 64 * (int)eg + 32 * hh, orr);
+              {
+                uint32_t orr[64];
+                ptx::tmem_ld_x32(tmem + lane_base + 128 * s + 64 * (int)eg, orr);
+                ptx::tmem_ld_x32(tmem + lane_base + 128 * s + 64 * (int)eg + 32, orr + 32);
                 ptx::tmem_wait_ld();
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
+                for (int u = 0; u < 32; ++u) {
                   const float a = __uint_as_float(orr[2 * u]) * inv, c = __uint_as_float(orr[2 * u + 1]) * inv;
-                  w[16 * hh + u] = BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
+                  w[u] = BF16 ? ptx::pack_bf16x2(a, c) : ptx::pack_f16x2(a, c);
                 }
               }
-              // the piece may still be read by the store of the previous slice / item: that wait overlaps the TMEM
-              // loads and packing above
-              if (ptx::lane_id() == 0) ptx::bulk_wait_group_read0();
-              __syncwarp();
+              if (t == 0) FFPA_STAMP(kidx, 8 + 3 * s);
+              if (epi_pending) {
+                // the piece is still being read by the bulk store of the previous slice (or of the previous item, when
+                // no KV tile was processed since); the wait overlaps the TMEM loads and packing above. Measured: storing
+                // the second slice with per-thread stores instead costs MORE (LSU back-pressure), see r02_fwd_epilogue.md
+                if (ptx::lane_id() == 0) ptx::bulk_wait_group_read0();
+                __syncwarp();
+              }
+              if (t == 0) FFPA_STAMP(kidx, 9 + 3 * s);
 #pragma unroll
               for (int v = 0; v < 8; ++v) {
                 const uint32_t addr = srow + (((uint32_t)v ^ (row & 7u)) << 4);
@@ -817,6 +895,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 ptx::tma_store_4d(&map_o, epi_base, dbox, fi.qoff + r0, h, fi.bt);
                 ptx::bulk_commit_group();
               }
+              if (t == 0) FFPA_STAMP(kidx, 10 + 3 * s);
               epi_pending = true;   // the piece goes back to the P ring: waited for before the next P tile is written
               continue;
             }
@@ -875,6 +954,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           else p.lse[((int64_t)b * p.heads_q + h) * p.lse_bh_stride + gq] = lse;
         }
         ptx::tc_fence_before();
+        if (t == 0) FFPA_STAMP(kidx, 6);
       }
     }
   }
