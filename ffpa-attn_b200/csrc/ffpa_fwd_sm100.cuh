@@ -26,6 +26,15 @@
 #ifndef FFPA_ALT_MAX_HD
 #define FFPA_ALT_MAX_HD 256
 #endif
+// Epilogue variant. 0 (default): the softmax warps store O themselves, staged in the idle P ring and written with TMA
+// bulk stores. 1: four extra warps (512 threads, setmaxnreg re-allocation) read the finished O tile out of TMEM -- parked
+// as a 16-bit copy in spare TMEM columns where there are any -- so the softmax warps go straight from the last KV tile
+// of an item to the first of the next one; they have no shared memory left to stage in and must use per-thread global
+// stores, whose LSU traffic costs more than the decoupling gains: measured 3-4 % SLOWER than variant 0 on causal /
+// short-sequence shapes, equal at C2 (profiles/r02_fwd_epilogue.md). Kept as a build option (-DFFPA_EPI_WARPS=1).
+#ifndef FFPA_EPI_WARPS
+#define FFPA_EPI_WARPS 0
+#endif
 #ifndef FFPA_UNIFIED_MIN_HD
 #define FFPA_UNIFIED_MIN_HD 512
 #endif
@@ -75,7 +84,13 @@ struct FwdCfg {
   // two-slab head dims carry one more warp: it TMA-stores the P tiles for the replay path (see FwdKernelParams)
   static constexpr int STORE_WARP = NSW + 2;
   static constexpr int V_WARP = NSW + 2;   // separate-ring head dims (<= 512): a second TMA producer warp streams V
-  static constexpr int THREADS = (NSW + 2 + ((DVP > 768 || HD <= FFPA_UNIFIED_MIN_HD) ? 1 : 0)) * 32;
+  // epilogue warps: warps 12..15 (a whole warpgroup, TMEM lane quarter = warp % 4); warps 8..11 = MMA, TMA, V / P-store,
+  // idle. Register file: 512 threads start with 128 registers; the two softmax warpgroups grow to 168, the producer /
+  // MMA warpgroup shrinks to 88 and the epilogue warpgroup to 80 (2 x 128 x 168 + 128 x 88 + 128 x 80 = 64512).
+  static constexpr bool EPIW = FFPA_EPI_WARPS != 0;
+  static constexpr int EPI_WARP0 = 12;
+  static constexpr int THREADS = EPIW ? 512 : (NSW + 2 + ((DVP > 768 || HD <= FFPA_UNIFIED_MIN_HD) ? 1 : 0)) * 32;
+  static_assert(!EPIW || NSW == 8, "the epilogue warpgroup layout assumes 8 softmax warps");
   static constexpr int P_BYTES = KSTG * 16384;
   // Wide heads keep Q resident (96-128 KB), leaving too little for separate K and V rings; they use
   // ONE ring of 16 KB stages shared by K stages and V slices (a slice = 2 consecutive stages), so
@@ -92,6 +107,11 @@ struct FwdCfg {
   static_assert(NKS >= 2, "not enough shared memory for the K ring");
   static_assert(!UNIFIED || (NKS % 2 == 0 && NKS >= 4), "unified ring needs an even number of stages");
   static_assert(S_BASE + 64 * KSTG <= 512 && S_BASE >= O_COLS, "O does not fit TMEM next to S");
+  // TMEM columns left over next to O and the S ring: when they hold the 16-bit copy of O (O_COLS / 2 columns) the
+  // epilogue warps first "park" the normalised tile there -- TMEM to TMEM, ~1000 cycles -- and release O for the next
+  // item's first PV MMA before they start the slow part, the global stores. -1: no room (head dims 320-384, 576-768).
+  static constexpr int PARK_BASE = (512 - (S_BASE + 64 * KSTG) >= O_COLS / 2) ? (S_BASE + 64 * KSTG)
+                                   : ((S_BASE - O_COLS >= O_COLS / 2) ? O_COLS : -1);
   // width of the O slab of pass `pass`, and N of its slice s
   __host__ __device__ static constexpr int slab_w(int pass) { return (DVP - pass * DSLAB) >= DSLAB ? DSLAB : (DVP - pass * DSLAB); }
   __host__ __device__ static constexpr int slice_n(int w, int s) { return (w - 256 * s) >= 256 ? 256 : 128; }
@@ -105,6 +125,7 @@ struct Barriers {
   uint64_t p_full[4], p_empty[4];
   uint64_t m_full[4];
   uint64_t p_written[4], p_stored[4];   // replay path: P tile complete in this CTA / drained by the store warp
+  uint64_t o_ready, inv_taken, o_free;  // epilogue warps: 1 / row sum published, ... consumed, O read out of TMEM (leader CTA)
 };
 
 __device__ __forceinline__ int num_kv_tiles(int causal, int nq, int nkv, int q0) {
@@ -234,9 +255,13 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   constexpr int kMmaWarp = Cfg::MMA_WARP, kTmaWarp = Cfg::TMA_WARP, kSoftmaxWarps = Cfg::NSW;
   constexpr int CQ = Cfg::CQ, CPT = Cfg::CPT;
   __shared__ float xch[2][Cfg::ALT ? 4 : 2 * Cfg::CQ][64];  // row-max exchange: [parity][kh*CQ+ch][row]  (ALT: [parity][wg*2+kh][row])
-  __shared__ float mval[Cfg::ALT ? 4 : 1][64];             // ALT: running row max published per tile (ring of 4)
+  __shared__ float mval[Cfg::ALT ? 4 : 1][Cfg::ALT ? 64 : 1];   // ALT: running row max published per tile (ring of 4)
   constexpr bool ALT = Cfg::ALT;
   __shared__ uint32_t tmem_slot;
+  __shared__ float epi_inv[Cfg::EPIW ? 64 : 1];   // 1 / row sum of the item handed to the epilogue warps
+  __shared__ float epi_lse[Cfg::EPIW ? 64 : 1];   // ... and its LSE: a global store issued by a softmax thread would make
+                                                  // the generic->async proxy fence of its next P tile wait behind the
+                                                  // epilogue warps' store traffic (profiles/r02_fwd_epilogue.md)
 
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();  // SWIZZLE_128B tiles need 1 KB alignment
@@ -265,6 +290,9 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       ptx::mbar_init(bar(bars.p_written[i]), kSoftmaxWarps);
       ptx::mbar_init(bar(bars.p_stored[i]), 1);
     }
+    ptx::mbar_init(bar(bars.o_ready), 2);     // softmax warps 0 and 1 (one writer per row)
+    ptx::mbar_init(bar(bars.inv_taken), 4);   // epilogue warps of this CTA
+    ptx::mbar_init(bar(bars.o_free), 8);      // epilogue warps of both CTAs
     ptx::fence_mbar_init();
   }
   if (warp == kTmaWarp && ptx::elect_one()) {
@@ -284,6 +312,152 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   const int group = p.heads_q / p.heads_kv;
 
+  if (Cfg::EPIW && warp >= (uint32_t)Cfg::EPI_WARP0) {
+    // =========================================== epilogue warps =================================
+    // O (fp32, TMEM) x 1 / row sum -> 16 bit -> global. Per item: wait for the row sums (o_ready) and for the last
+    // PV MMA (p_empty of the last tile), read O, hand TMEM back (o_free, awaited by the MMA issuer before the first
+    // PV MMA of the next item), store. Every lane owns another row, so a store instruction is 32 LSU wavefronts: slow,
+    // but no longer between two items of the softmax warps.
+    if constexpr (Cfg::EPIW) {
+      ptx::setmaxnreg_dec<80>();
+      const uint32_t lane128 = (warp & 3u) * 32u + ptx::lane_id();
+      const uint32_t row = lane128 & 63u, kh = lane128 >> 6;
+      const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
+      const uint32_t l_o_free = ptx::mapa(bar(bars.o_free), 0);
+      uint32_t g = 0, it = 0;
+      for (uint32_t kidx = 0;; ++kidx) {
+        const int item_s = next_item(p, cluster, nclusters, kidx);
+        if (item_s < 0) break;
+        const FwdItem fi = decode_fwd_item<Cfg::NPASS>(p, (uint32_t)item_s);
+        if (fi.T <= 0) continue;
+        const uint32_t gl = g + (uint32_t)fi.T - 1;
+        g += (uint32_t)fi.T;
+        const int h = fi.bh % p.heads_q, b = fi.bh / p.heads_q;
+        const int gq = fi.mt * 128 + 64 * (int)rank + (int)row;
+        const bool row_ok = gq < fi.nq;
+        const int dv0 = fi.pass * Cfg::DSLAB, dvw = Cfg::slab_w(fi.pass);
+        uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
+                        2 * ((int64_t)fi.bt * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)(fi.qoff + gq) * p.o_stride[2]);
+        const bool o_al32 = (reinterpret_cast<uintptr_t>(orow) & 31u) == 0;
+        ptx::mbar_wait(bar(bars.o_ready), it & 1);
+        const float inv = epi_inv[row];
+        const float lse = epi_lse[row];
+        __syncwarp();
+        if (ptx::lane_id() == 0) ptx::mbar_arrive(bar(bars.inv_taken));
+        if (kh == 0 && row_ok) {
+          if (Cfg::NPASS == 2 && p.stash_p != nullptr) p.stash_inv[(int64_t)fi.bh * p.n_mt_even * 128 + gq] = inv;
+          if ((p.lse != nullptr || p.kv_splits > 1) && fi.pass == 0) {
+            if (p.kv_splits > 1) p.part_lse[(((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq] = lse;
+            else if (p.cu_q != nullptr) p.lse[(int64_t)h * p.total_q + fi.qoff + gq] = lse;   // [Hq, total_q]
+            else p.lse[((int64_t)b * p.heads_q + h) * p.lse_bh_stride + gq] = lse;
+          }
+        }
+        ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
+        ptx::tc_fence_after();
+        if (threadIdx.x == Cfg::EPI_WARP0 * 32) FFPA_STAMP(kidx, 5);
+        // 32 head dims (16 packed registers) of this row -> global
+        auto store32 = [&](const uint32_t* w, int d0) {
+          if (!row_ok) return;
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int d = d0 + 16 * v;
+            if (o_al32 && d + 16 <= p.head_dim) {
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + 2 * d), "r"(w[8 * v]), "r"(w[8 * v + 1]),
+                           "r"(w[8 * v + 2]), "r"(w[8 * v + 3]), "r"(w[8 * v + 4]), "r"(w[8 * v + 5]), "r"(w[8 * v + 6]), "r"(w[8 * v + 7])
+                           : "memory");
+            } else {
+              if (d < p.head_dim) *reinterpret_cast<uint4*>(orow + 2 * d) = make_uint4(w[8 * v], w[8 * v + 1], w[8 * v + 2], w[8 * v + 3]);
+              if (d + 8 < p.head_dim)
+                *reinterpret_cast<uint4*>(orow + 2 * d + 16) = make_uint4(w[8 * v + 4], w[8 * v + 5], w[8 * v + 6], w[8 * v + 7]);
+            }
+          }
+        };
+        auto release_o = [&]() {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (ptx::lane_id() == 0) ptx::mbar_arrive_cluster(l_o_free);
+          if (threadIdx.x == Cfg::EPI_WARP0 * 32) FFPA_STAMP(kidx, 8);
+        };
+        constexpr uint32_t kPark = Cfg::PARK_BASE >= 0 ? (uint32_t)Cfg::PARK_BASE : 0u;
+        if (Cfg::PARK_BASE >= 0 && p.kv_splits == 1) {
+          // phase 1: park the normalised 16-bit tile in the spare TMEM columns, release O
+#pragma unroll
+          for (int s = 0; s < Cfg::NSLICE; ++s) {
+            if (256 * s >= dvw) break;
+            const int half = Cfg::slice_n(dvw, s) / 2;   // columns of this slice per lane: 128 or 64
+#pragma unroll 1
+            for (int c = 0; c < half; c += 32) {
+              uint32_t orr[32], w[16];
+              ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c, orr);
+              ptx::tmem_wait_ld();
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const float a = __uint_as_float(orr[2 * u]) * inv, c2 = __uint_as_float(orr[2 * u + 1]) * inv;
+                w[u] = BF16 ? ptx::pack_bf16x2(a, c2) : ptx::pack_f16x2(a, c2);
+              }
+              ptx::tmem_st_x16(tmem + lane_base + kPark + (128 * s + c) / 2, w);
+            }
+          }
+          ptx::tmem_wait_st();
+          release_o();
+          // phase 2: parked tile -> global
+#pragma unroll
+          for (int s = 0; s < Cfg::NSLICE; ++s) {
+            if (256 * s >= dvw) break;
+            const int half = Cfg::slice_n(dvw, s) / 2;
+#pragma unroll 1
+            for (int c = 0; c < half; c += 64) {
+              uint32_t w[32];
+              ptx::tmem_ld_x32(tmem + lane_base + kPark + (128 * s + c) / 2, w);
+              ptx::tmem_wait_ld();
+              store32(w, dv0 + 256 * s + half * (int)kh + c);
+              store32(w + 16, dv0 + 256 * s + half * (int)kh + c + 32);
+            }
+          }
+          ptx::tc_fence_before();   // the parked copy is rewritten by the next item's phase 1 (same thread, program order)
+        } else {
+          // no spare TMEM columns (or fp32 partials of a KV split): O is released after its last load
+#pragma unroll
+          for (int s = 0; s < Cfg::NSLICE; ++s) {
+            if (256 * s >= dvw) break;
+            const int half = Cfg::slice_n(dvw, s) / 2;
+            const bool last_slice = (256 * (s + 1) >= dvw);
+#pragma unroll 1
+            for (int c = 0; c < half; c += 32) {
+              uint32_t orr[32];
+              ptx::tmem_ld_x32(tmem + lane_base + 128 * s + c, orr);
+              ptx::tmem_wait_ld();
+              if (last_slice && c + 32 >= half) release_o();
+              const int d0 = dv0 + 256 * s + half * (int)kh + c;
+              if (p.kv_splits > 1) {
+                // fp32 partial of this KV split, normalised by its own row sum
+                if (row_ok) {
+                  float* po = p.part_o + ((((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq) * (int64_t)p.head_dim;
+#pragma unroll
+                  for (int v = 0; v < 8; ++v)
+                    if (d0 + 4 * v < p.head_dim)
+                      *reinterpret_cast<float4*>(po + d0 + 4 * v) =
+                          make_float4(__uint_as_float(orr[4 * v]) * inv, __uint_as_float(orr[4 * v + 1]) * inv,
+                                      __uint_as_float(orr[4 * v + 2]) * inv, __uint_as_float(orr[4 * v + 3]) * inv);
+                }
+              } else {
+                uint32_t w[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                  const float a = __uint_as_float(orr[2 * u]) * inv, c2 = __uint_as_float(orr[2 * u + 1]) * inv;
+                  w[u] = BF16 ? ptx::pack_bf16x2(a, c2) : ptx::pack_f16x2(a, c2);
+                }
+                store32(w, d0);
+              }
+            }
+          }
+        }
+        if (threadIdx.x == Cfg::EPI_WARP0 * 32) FFPA_STAMP(kidx, 6);
+        ++it;
+      }
+    }
+  } else if (warp >= (uint32_t)kSoftmaxWarps) {
+  if constexpr (Cfg::EPIW) ptx::setmaxnreg_dec<88>();
   if (warp == kTmaWarp) {
     // =========================================== TMA producer: Q and K (and V on the shared ring) ===========
     // Separate rings (head dims <= 512): this thread streams Q and K only and the V warp below streams V, so neither
@@ -459,6 +633,10 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
           if (step >= LA) {
             const uint32_t pbuf = gp % KS;
+            if constexpr (Cfg::EPIW) {
+              // the first PV MMA of an item overwrites O: the epilogue warps must have read the previous item's tile
+              if (step == LA) ptx::mbar_wait_cluster(bar(bars.o_free), (it & 1) ^ 1);
+            }
             ptx::mbar_wait_cluster(bar(bars.p_full[pbuf]), (gp / KS) & 1);
             ptx::tc_fence_after();
             if (step == LA) FFPA_STAMP(kidx, 1);
@@ -529,8 +707,10 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       ptx::bulk_wait_group0();
     }
     __syncwarp();
+  }
   } else {
     // =========================================== softmax / correction / epilogue ================
+    if constexpr (Cfg::EPIW) ptx::setmaxnreg_inc<168>();
     // NSW*32 threads: TMEM lane = t % 128; warpgroup ch = t / 128 owns S columns [CPT*ch, CPT*ch+CPT).
     const uint32_t t = threadIdx.x;
     const uint32_t lane128 = t & 127;
@@ -548,6 +728,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint32_t g = 0;                      // global tile counter at the start of the item (ALT) / running (column split)
     uint32_t uw = 0;                     // ALT: tiles processed by this warpgroup
     uint32_t pub[4] = {0, 0, 0, 0};      // ALT: completed publications of m_full[0..3]
+    uint32_t itn = 0;                    // non-empty items finished (phase of the epilogue-warp barriers)
     bool epi_pending = false;            // a bulk store of the last epilogue may still be reading the P ring
     // the next item is looked up and decoded (schedule-table load, integer divisions: ~1000 cycles) while this item's
     // last PV MMA drains, not between the epilogue and the first softmax of the next item where nothing hides it
@@ -807,14 +988,21 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           ptx::named_bar_sync(5 + rgrp, 128);
           l_tot = (xch[0][0][row] + xch[0][1][row]) + (xch[0][2][row] + xch[0][3][row]);
           ptx::named_bar_sync(5 + rgrp, 128);
-          ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
-          ptx::tc_fence_after();
+          if constexpr (!Cfg::EPIW) {
+            ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
+            ptx::tc_fence_after();
+          }
         } else {
         gl = g - 1;
-        ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
-        ptx::tc_fence_after();
-        // row-sum exchange reuses the max-exchange buffer of the last tile: every thread of the
-        // row group finished reading it before PV(gl) could retire (p_full precedes p_empty).
+        // row-sum exchange reuses the max-exchange buffer of the last tile: every thread of the row group must have
+        // finished reading it. Without epilogue warps the wait for PV(gl) (needed to read O anyway) implies that
+        // (p_full precedes p_empty); with them the softmax warps do not wait for the MMA: one more named barrier.
+        if constexpr (Cfg::EPIW) {
+          ptx::named_bar_sync(1 + rgrp, kSoftmaxWarps * 16);
+        } else {
+          ptx::mbar_wait(bar(bars.p_empty[gl % KS]), (gl / KS) & 1);
+          ptx::tc_fence_after();
+        }
         float (*xl)[64] = xch[gl & 1];
         xl[slot][row] = l;
         ptx::named_bar_sync(1 + rgrp, kSoftmaxWarps * 16);
@@ -824,8 +1012,21 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (t == 0) FFPA_STAMP(kidx, 5);
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
         const bool row_ok = gq < seq_q;
-        if (Cfg::NPASS == 2 && p.stash_p != nullptr && wgi == 0 && kh == 0)
+        if (!Cfg::EPIW && Cfg::NPASS == 2 && p.stash_p != nullptr && wgi == 0 && kh == 0)
           p.stash_inv[(int64_t)bh * p.n_mt_even * 128 + gq] = inv;
+        if constexpr (Cfg::EPIW) {
+          // hand the tile to the epilogue warps: 1 / row sum and LSE per row (one writer per row: warps 0 and 1)
+          if (wgi == 0 && kh == 0) {
+            ptx::mbar_wait(bar(bars.inv_taken), (itn & 1) ^ 1);   // the previous item's values have been read
+            epi_inv[row] = inv;
+            // natural-log LSE; rows without any visible key: O = 0, LSE = -inf
+            epi_lse[row] = (l_tot > 0.f) ? (m * mul + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
+            __syncwarp();
+            if (ptx::lane_id() == 0) ptx::mbar_arrive(bar(bars.o_ready));
+          }
+          ++itn;
+        }
+        if constexpr (!Cfg::EPIW) {
         uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) +
                         2 * ((int64_t)fi.bt * p.o_stride[0] + (int64_t)h * p.o_stride[1] + (int64_t)(fi.qoff + gq) * p.o_stride[2]);
         const bool o_al32 = (reinterpret_cast<uintptr_t>(orow) & 31u) == 0;   // 32-byte stores need it (strides are only 16-byte granular)
@@ -946,7 +1147,8 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
         }
-        if ((p.lse != nullptr || p.kv_splits > 1) && wgi == 0 && kh == 0 && row_ok && pass == 0) {
+        }  // !EPIW
+        if (!Cfg::EPIW && (p.lse != nullptr || p.kv_splits > 1) && wgi == 0 && kh == 0 && row_ok && pass == 0) {
           // natural-log LSE; rows without any visible key: O = 0, LSE = -inf
           const float lse = (l_tot > 0.f) ? (m * mul + log2f(l_tot)) * 0.6931471805599453f : NEG_INF;
           if (p.kv_splits > 1) p.part_lse[(((int64_t)fi.split * p.batch + b) * p.heads_q + h) * p.seqlen_q + gq] = lse;
@@ -959,7 +1161,7 @@ ffpa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   }
 
-  if (warp < (uint32_t)kSoftmaxWarps && ptx::lane_id() == 0) ptx::bulk_wait_group0();   // O tiles stored by the epilogue
+  if (!Cfg::EPIW && warp < (uint32_t)kSoftmaxWarps && ptx::lane_id() == 0) ptx::bulk_wait_group0();   // O tiles stored by the epilogue
   ptx::tc_fence_before();
   ptx::cluster_sync();
   if (warp == kMmaWarp) ptx::tmem_dealloc<CG>(tmem, 512);
